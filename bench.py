@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- compress+decompress throughput of the blocked shuffle->LZ hot path on B200.
+
+Workload (N=1): BASELINE.json configs[1] -- LZ4 + byte-shuffle, clevel 5, typesize 4, one
+256 MiB bench.c-shaped buffer (bench/bench.c:141-170).  A step = one blosc_compress_ctx +
+one blosc_decompress_ctx of that buffer.  `value` = (bytes compressed + bytes decompressed) /
+time with the buffers resident in HBM; `e2e` = the same through the C ABI with pinned HOST
+buffers (H2D/D2H inside the timed region).  N>1: one process per GPU, each rank owns its own
+256 MiB chunk (chunks are independent: no data-path collective, weak scaling); the time is the
+max over ranks.  `--impl reference` times the reference's own CPU implementation (oracle/_ref,
+all host threads) on the same config.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (compressor, doshuffle, typesize, clevel, nbytes)
+    "lz4-shuffle-ts4-cl5-256MiB": ("lz4", 1, 4, 5, 256 << 20),
+    "blosclz-bitshuffle-ts8-cl5-256MiB": ("blosclz", 2, 8, 5, 256 << 20),
+}
+DEFAULT_WORKLOAD = "lz4-shuffle-ts4-cl5-256MiB"
+METRIC = "compress+decompress GB/s"
+
+
+def bench_words(nbytes, np):
+    i = np.arange(nbytes // 4, dtype=np.uint32)
+    w = ((i << np.uint32(26)) ^ (i << np.uint32(18)) ^ (i << np.uint32(11)) ^ (i << np.uint32(3)) ^ i) & np.uint32((1 << 19) - 1)
+    return w.view(np.uint8)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[2 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_ref():
+    path = os.path.join(ROOT, "oracle", "_ref", "libblosc_ref.so")
+    kind = "reference"
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        kind = "port"
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
+    lib = C.CDLL(path)
+    pre = "blosc_" if kind == "reference" else "orc_"
+    comp = getattr(lib, pre + "compress_ctx"); comp.restype = C.c_int
+    dec = getattr(lib, pre + "decompress_ctx"); dec.restype = C.c_int
+    return kind, comp, dec
+
+
+def cpu_roundtrip(np, workload, nthreads, repeats):
+    """Reference CPU implementation (AVX2 build, its own pthread pool) on the host cores."""
+    comp_name, shuf, ts, clevel, nbytes = WORKLOADS[workload]
+    kind, comp, dec = load_ref()
+    if kind == "port":
+        nthreads = 1
+    src = bench_words(nbytes, np).copy()
+    chunk = np.zeros(nbytes + 16, np.uint8)
+    out = np.zeros(nbytes, np.uint8)
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+
+    def once():
+        t0 = time.perf_counter()
+        cb = comp(ci(clevel), ci(shuf), sz(ts), sz(nbytes), src.ctypes.data_as(vp), chunk.ctypes.data_as(vp), sz(nbytes + 16),
+                  comp_name.encode(), sz(0), ci(nthreads))
+        t1 = time.perf_counter()
+        nb = dec(chunk.ctypes.data_as(vp), out.ctypes.data_as(vp), sz(nbytes), ci(nthreads))
+        t2 = time.perf_counter()
+        assert cb > 0 and nb == nbytes
+        return t1 - t0, t2 - t1, cb
+    t_w = time.perf_counter()                # warm pages, thread creation and the host's clock/cgroup ramp:
+    nwarm = 0                                # the first second of calls runs several times slower than steady state
+    while nwarm < 3 or time.perf_counter() - t_w < 2.0:
+        once(); nwarm += 1
+    tc = td = 0.0
+    for _ in range(repeats):
+        a, b, cb = once()
+        tc += a; td += b
+    assert (out == src).all()
+    return {"kind": kind, "cores": nthreads, "tc": tc / repeats, "td": td / repeats, "cbytes": cb, "nbytes": nbytes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    args = ap.parse_args()
+    import numpy as np
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    comp_name, shuf, ts, clevel, nbytes = WORKLOADS[args.workload]
+    host_threads = args.cpu_threads or min(len(os.sched_getaffinity(0)) or 1, 256)
+    config = {"workload": args.workload, "codec": comp_name, "filter": ["none", "shuffle", "bitshuffle"][shuf], "typesize": ts,
+              "clevel": clevel, "chunk_bytes": nbytes, "chunks_per_gpu": 1, "sharding": "one independent chunk per GPU",
+              "l2": "input (256 MiB) larger than the 126 MB L2, no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_roundtrip(np, args.workload, host_threads, max(1, args.steps))
+        t = r["tc"] + r["td"]
+        val = 2 * nbytes / t / 1e9
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": config,
+                "compress_gbs": nbytes / r["tc"] / 1e9, "decompress_gbs": nbytes / r["td"] / 1e9, "ratio": nbytes / r["cbytes"],
+                "cpu_baseline": {"value": val, "unit": "GB/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": f"{max(1, args.steps)} x (compress+decompress) of the full {nbytes >> 20} MiB buffer"},
+                "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    if world > 1:
+        os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", ",".join(str(i) for i in range(world))).split(",")[local_rank]
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", 0 if world > 1 else local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    src_h = torch.from_numpy(bench_words(nbytes, np).copy()).pin_memory()
+    chunk_h = torch.zeros(nbytes + 16, dtype=torch.uint8).pin_memory()
+    out_h = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+    d_src = src_h.to(dev)
+    d_chunk = torch.zeros(nbytes + 16, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        cb = pkg.compress_ctx(clevel, shuf, ts, nbytes, d_src, d_chunk, nbytes + 16, comp_name)
+        nb = pkg.decompress_ctx(d_chunk, d_out, nbytes)
+        return cb, nb
+
+    def step_host():
+        cb = pkg.compress_ctx(clevel, shuf, ts, nbytes, src_h, chunk_h, nbytes + 16, comp_name)
+        nb = pkg.decompress_ctx(chunk_h, out_h, nbytes)
+        return cb, nb
+
+    def timed(fn, steps):
+        """CUDA events around the whole region (the API calls are synchronous: each returns after
+        its own stream has drained, so the events bracket all device work of the steps)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        tc = td = 0.0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            cb = pkg.compress_ctx(*fn[0])
+            t1 = time.perf_counter()
+            nb = pkg.decompress_ctx(*fn[1])
+            t2 = time.perf_counter()
+            tc += t1 - t0; td += t2 - t1
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, tc, td], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, tc, td = t.tolist()
+        barrier()
+        return ms, tc, td, cb, nb
+
+    dev_args = ((clevel, shuf, ts, nbytes, d_src, d_chunk, nbytes + 16, comp_name), (d_chunk, d_out, nbytes))
+    host_args = ((clevel, shuf, ts, nbytes, src_h, chunk_h, nbytes + 16, comp_name), (chunk_h, out_h, nbytes))
+
+    for _ in range(max(3, args.warmup)):
+        cb, nb = step_dev()
+        assert cb > 0 and nb == nbytes
+    assert torch.equal(d_out, d_src), "round trip mismatch"
+    step_host()
+    assert torch.equal(out_h, src_h), "host round trip mismatch"
+
+    # timed region 1: device-resident (`value`), kernel events on, clocks sampled
+    sampler = ClockSampler(local_rank if world > 1 else torch.cuda.current_device())
+    pkg.set_profiling(True)
+    pkg.prof_reset()
+    launches0 = pkg.launch_count()
+    sampler.start()
+    ms, tc, td, cb, nb = timed(dev_args, args.steps)
+    clocks = sampler.stop()
+    launches = pkg.launch_count() - launches0
+    prof = pkg.prof_get()
+    pkg.set_profiling(False)
+    assert cb > 0 and nb == nbytes
+
+    # timed region 2: end to end from/to pinned host memory through the C ABI
+    ms_h, tc_h, td_h, cb_h, nb_h = timed(host_args, args.steps)
+    assert cb_h == cb and nb_h == nbytes and torch.equal(out_h, src_h)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, hbm_src = peaks()
+    per_step = ms / args.steps / 1e3
+    value = world * 2 * nbytes / per_step / 1e9
+    e2e_value = world * 2 * nbytes / (ms_h / args.steps / 1e3) / 1e9
+    # dominant kernel = the LZ encoder (one launch per step); algorithmic bytes per launch = nbytes read + cbytes written
+    enc_ms, enc_n = prof["encode"]
+    dec_ms, dec_n = prof["decode"]
+    enc_avg = enc_ms / max(enc_n, 1) / 1e3
+    achieved = (nbytes + cb) / enc_avg / 1e9 if enc_avg > 0 else 0.0
+    kernels = {k: {"ms_avg": (v[0] / v[1] if v[1] else 0.0), "launches": v[1]} for k, v in prof.items()}
+    cpu = cpu_roundtrip(np, args.workload, host_threads, 3) if world == 1 else None
+    line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config,
+            "compress_gbs": world * nbytes / (tc / args.steps) / 1e9, "decompress_gbs": world * nbytes / (td / args.steps) / 1e9,
+            "ratio": nbytes / cb, "cbytes": cb,
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": nbytes + cb, "d2h_bytes_per_step": cb + nbytes,
+                    "compress_gbs": world * nbytes / (tc_h / args.steps) / 1e9, "decompress_gbs": world * nbytes / (td_h / args.steps) / 1e9},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "encode_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_launch": nbytes + cb, "avg_launch_ms": enc_avg * 1e3,
+                         "decode_kernel": {"achieved": (nbytes + cb) / (dec_ms / max(dec_n, 1) / 1e3) / 1e9 if dec_ms else 0.0,
+                                           "avg_launch_ms": dec_ms / max(dec_n, 1)}},
+            "kernels": kernels}
+    if cpu:
+        t = cpu["tc"] + cpu["td"]
+        line["cpu_baseline"] = {"value": 2 * nbytes / t / 1e9, "unit": "GB/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                "sample": f"3 x (compress+decompress) of the full {nbytes >> 20} MiB buffer, blosc_*_ctx with nthreads={cpu['cores']}",
+                                "compress_gbs": nbytes / cpu["tc"] / 1e9, "decompress_gbs": nbytes / cpu["td"] / 1e9}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""c-blosc_b200 -- Python host-side mirror of the c-blosc C API over libblosc_b200.so.
+
+The product is the C-ABI shared library (``include/blosc_b200.h``,
+``c-blosc_b200/csrc``); this module is a thin ctypes binding that keeps the reference's
+names, argument order and return codes (reference ``blosc/blosc.h:221-312``) so tests read
+like the reference's own.  Buffers may be ``bytes``/``bytearray``/numpy arrays (host
+pointers) or torch CUDA tensors (device pointers); the library tells them apart itself.
+
+The directory name contains a hyphen (it is the name the build contract asks for), so it
+is loaded with importlib under the module name ``cblosc_b200`` -- see
+``__graft_entry__.load_package()``.
+
+There is deliberately no fallback: if the CUDA library is missing this import raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libblosc_b200.so")
+
+BLOSC_NOSHUFFLE, BLOSC_SHUFFLE, BLOSC_BITSHUFFLE = 0, 1, 2
+BLOSC_MAX_OVERHEAD = 16
+FILT_SHUFFLE, FILT_UNSHUFFLE, FILT_BITSHUFFLE, FILT_BITUNSHUFFLE = 0, 1, 2, 3
+KERNEL_KINDS = ("filter", "encode", "scan", "compact", "decode", "unfilter")
+
+
+def _load(path: str) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  c-blosc_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+    lib.blosc_compress_ctx.restype = ci
+    lib.blosc_compress_ctx.argtypes = [ci, ci, sz, sz, vp, vp, sz, C.c_char_p, sz, ci]
+    lib.blosc_decompress_ctx.restype = ci
+    lib.blosc_decompress_ctx.argtypes = [vp, vp, sz, ci]
+    lib.blosc_getitem.restype = ci
+    lib.blosc_getitem.argtypes = [vp, ci, ci, vp]
+    lib.blosc_compress.restype = ci
+    lib.blosc_compress.argtypes = [ci, ci, sz, sz, vp, vp, sz]
+    lib.blosc_decompress.restype = ci
+    lib.blosc_decompress.argtypes = [vp, vp, sz]
+    lib.blosc_b200_filter.restype = ci
+    lib.blosc_b200_filter.argtypes = [ci, sz, sz, vp, vp]
+    lib.blosc_b200_set_profiling.argtypes = [ci]
+    lib.blosc_b200_prof_get.argtypes = [ci, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.blosc_b200_launch_count.restype = C.c_longlong
+    lib.blosc_set_compressor.argtypes = [C.c_char_p]
+    lib.blosc_set_splitmode.argtypes = [ci]
+    lib.blosc_set_blocksize.argtypes = [sz]
+    lib.blosc_cbuffer_sizes.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    return lib
+
+
+lib = _load(os.environ.get("BLOSC_B200_LIB", LIB_PATH))
+
+
+def _ptr(buf):
+    """Raw address of a host buffer (bytes-like / numpy) or a torch tensor (host or CUDA)."""
+    if buf is None:
+        return None
+    if isinstance(buf, int):
+        return buf
+    if hasattr(buf, "data_ptr"):            # torch.Tensor
+        return buf.data_ptr()
+    if hasattr(buf, "ctypes"):              # numpy
+        return buf.ctypes.data
+    if isinstance(buf, bytes):              # points into the bytes object; caller keeps it alive
+        return C.cast(C.c_char_p(buf), C.c_void_p).value
+    if isinstance(buf, bytearray):
+        return C.addressof((C.c_char * len(buf)).from_buffer(buf))
+    raise TypeError(f"unsupported buffer type {type(buf)}")
+
+
+def compress_ctx(clevel, doshuffle, typesize, nbytes, src, dest, destsize, compressor, blocksize=0, numinternalthreads=1):
+    """blosc_compress_ctx (reference blosc.h:245-248)."""
+    return lib.blosc_compress_ctx(clevel, doshuffle, typesize, nbytes, _ptr(src), _ptr(dest), destsize,
+                                  compressor.encode() if isinstance(compressor, str) else compressor,
+                                  blocksize, numinternalthreads)
+
+
+def decompress_ctx(src, dest, destsize, numinternalthreads=1):
+    """blosc_decompress_ctx (reference blosc.h:301-302)."""
+    return lib.blosc_decompress_ctx(_ptr(src), _ptr(dest), destsize, numinternalthreads)
+
+
+def getitem(src, start, nitems, dest):
+    """blosc_getitem (reference blosc.h:312)."""
+    return lib.blosc_getitem(_ptr(src), start, nitems, _ptr(dest))
+
+
+def filter_block(mode, typesize, blocksize, src, dest):
+    """One filter over one block (GPU counterpart of blosc_internal_{,un}{,bit}shuffle)."""
+    return lib.blosc_b200_filter(mode, typesize, blocksize, _ptr(src), _ptr(dest))
+
+
+def set_profiling(on: bool):
+    lib.blosc_b200_set_profiling(1 if on else 0)
+
+
+def prof_reset():
+    lib.blosc_b200_prof_reset()
+
+
+def prof_get():
+    """{kind: (total_ms, launches)} measured with CUDA events on the launching stream."""
+    out = {}
+    for i, k in enumerate(KERNEL_KINDS):
+        ms, n = C.c_double(0), C.c_longlong(0)
+        lib.blosc_b200_prof_get(i, C.byref(ms), C.byref(n))
+        out[k] = (ms.value, n.value)
+    return out
+
+
+def launch_count() -> int:
+    return int(lib.blosc_b200_launch_count())

@@ -1,0 +1,182 @@
+/*
+ * backend_cuda.cu -- CUDA (sm_100a) implementation of b2_backend.h: kernel launches,
+ * device memory, streams, per-kernel event timing.  Compiled with
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+ * Grid sizing: the codec kernels launch one warp per LZ stream and let the hardware
+ * scheduler keep all 148 SMs busy (12 LZ4 warps / 3 BloscLZ warps resident per SM, the
+ * limit being the shared-memory hash tables); the bandwidth-bound filter kernel runs a
+ * grid-stride loop over 148 x 8 CTAs.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "b2_backend.h"
+#include "dev_chunk.cuh"
+#include "dev_filters.cuh"
+
+struct b2_stream_s {
+  cudaStream_t s;
+};
+
+static int g_num_sms = 148;
+static int g_prof_on = 0;
+static double g_prof_ms[B2_K_COUNT];
+static long long g_prof_n[B2_K_COUNT];
+static long long g_launches = 0;
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      fprintf(stderr, "blosc_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return -1;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+/* per-device one-time setup (opt-in to > 48 KiB dynamic shared memory) */
+extern "C" int b2_device_prepare(void) {
+  CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
+  return 0;
+}
+
+extern "C" int b2_backend_init(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return -1; }
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, dev));
+  g_num_sms = p.multiProcessorCount;
+  return b2_device_prepare();
+}
+
+extern "C" int b2_get_device(void) { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return 0; } return d; }
+extern "C" int b2_set_device(int dev) { CK(cudaSetDevice(dev)); return 0; }
+
+extern "C" int b2_stream_create(b2_stream_t* s) {
+  b2_stream_s* st = new b2_stream_s;
+  if (cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking) != cudaSuccess) { delete st; return -1; }
+  *s = st;
+  return 0;
+}
+extern "C" void b2_stream_destroy(b2_stream_t s) { if (s) { cudaStreamDestroy(s->s); delete s; } }
+extern "C" int b2_stream_sync(b2_stream_t s) { CK(cudaStreamSynchronize(s ? s->s : 0)); return 0; }
+
+extern "C" int b2_dev_alloc(void** p, size_t n) { CK(cudaMalloc(p, n)); return 0; }
+extern "C" void b2_dev_free(void* p) { cudaFree(p); }
+extern "C" int b2_pinned_alloc(void** p, size_t n) { CK(cudaMallocHost(p, n)); return 0; }
+extern "C" void b2_pinned_free(void* p) { cudaFreeHost(p); }
+
+extern "C" int b2_ptr_is_device(const void* p) {
+  cudaPointerAttributes a;
+  if (p == NULL) return 0;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int b2_copy_h2d(void* d, const void* h, size_t n, b2_stream_t s) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s->s)); return 0; }
+extern "C" int b2_copy_d2h(void* h, const void* d, size_t n, b2_stream_t s) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s->s)); return 0; }
+extern "C" int b2_copy_d2d(void* d, const void* s_, size_t n, b2_stream_t s) { CK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s->s)); return 0; }
+extern "C" int b2_memset_dev(void* d, int v, size_t n, b2_stream_t s) { CK(cudaMemsetAsync(d, v, n, s->s)); return 0; }
+
+/* ---- profiling: CUDA events recorded on the launching stream around every kernel;
+ * nothing synchronises until the numbers are read (b2_prof_get), so profiling can stay
+ * on inside a timed region. ---- */
+#include <mutex>
+#include <vector>
+struct PendingEv { cudaEvent_t e0, e1; int kind; };
+static std::vector<PendingEv> g_pending;
+static std::mutex g_prof_mu;
+
+struct ProfScope {
+  cudaEvent_t e0, e1;
+  int kind;
+  cudaStream_t s;
+  bool on;
+  ProfScope(int k, cudaStream_t st) : kind(k), s(st), on(g_prof_on != 0) {
+    if (on) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+  }
+  ~ProfScope() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_launches++;
+    if (on) { cudaEventRecord(e1, s); g_pending.push_back({e0, e1, kind}); }
+  }
+};
+
+static void prof_resolve() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& p : g_pending) {
+    float ms = 0;
+    cudaEventSynchronize(p.e1);
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    g_prof_ms[p.kind] += ms; g_prof_n[p.kind]++;
+    cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+  }
+  g_pending.clear();
+}
+
+extern "C" void b2_prof_enable(int on) { g_prof_on = on; }
+extern "C" void b2_prof_reset(void) { prof_resolve(); for (int i = 0; i < B2_K_COUNT; i++) { g_prof_ms[i] = 0; g_prof_n[i] = 0; } }
+extern "C" int b2_prof_get(int kind, double* ms, long long* n) {
+  if (kind < 0 || kind >= B2_K_COUNT) return -1;
+  prof_resolve();
+  if (ms) *ms = g_prof_ms[kind];
+  if (n) *n = g_prof_n[kind];
+  return 0;
+}
+extern "C" long long b2_launch_count(void) { return g_launches; }
+
+extern "C" int b2_launch_filter(const FilterArgs* a, b2_stream_t s) {
+  const bool bit = a->mode >= FILT_BITSHUFFLE;
+  const bool inverse = a->mode == FILT_UNSHUFFLE || a->mode == FILT_BITUNSHUFFLE;
+  const long long nblocks = (a->nbytes + a->blocksize - 1) / a->blocksize;
+  const long long ipb = (a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1;
+  long long ctas = (nblocks * ipb + FILT_WARPS - 1) / FILT_WARPS;
+  const long long cap = (long long)g_num_sms * 8;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  ProfScope ps(inverse ? B2_K_UNFILTER : B2_K_FILTER, s->s);
+  filter_kernel<<<(unsigned)ctas, FILT_WARPS * 32, bit ? FILT_WARPS * 16 * FILT_TILE : 0, s->s>>>(*a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2_launch_encode(const EncodeArgs* a, b2_stream_t s) {
+  int wpc = 65536 / a->table_bytes;           /* 64 KiB of tables per CTA -> 3 CTAs per SM */
+  if (wpc > 4) wpc = 4;
+  if (wpc < 1) wpc = 1;
+  const int ctas = (a->map.nstreams + wpc - 1) / wpc;
+  if (ctas <= 0) return 0;
+  ProfScope ps(B2_K_ENCODE, s->s);
+  encode_kernel<<<ctas, wpc * 32, (size_t)wpc * a->table_bytes, s->s>>>(*a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2_launch_scan(const ScanArgs* a, b2_stream_t s) {
+  ProfScope ps(B2_K_SCAN, s->s);
+  scan_kernel<<<1, SCAN_THREADS, 0, s->s>>>(*a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2_launch_compact(const CompactArgs* a, b2_stream_t s) {
+  int ctas = a->nblocks;
+  if (ctas > g_num_sms * 8) ctas = g_num_sms * 8;
+  if (ctas <= 0) return 0;
+  ProfScope ps(B2_K_COMPACT, s->s);
+  compact_kernel<<<ctas, COMPACT_THREADS, 0, s->s>>>(*a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2_launch_decode(const DecodeArgs* a, b2_stream_t s) {
+  const int wpc = 4;
+  const int ctas = (a->map.nstreams + wpc - 1) / wpc;
+  if (ctas <= 0) return 0;
+  ProfScope ps(B2_K_DECODE, s->s);
+  decode_kernel<<<ctas, wpc * 32, 0, s->s>>>(*a);
+  CK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,724 @@
+/*
+ * blosc_b200.c -- host side of libblosc_b200: the c-blosc 1.x C API and the chunk
+ * framing / planning, in plain C, over the device layer of b2_backend.h.
+ *
+ * What stays on the host (it is the format contract, a few dozen integer operations per
+ * call): argument validation and return codes (reference blosc/blosc.c:1062-1145,
+ * 1435-1518), compute_blocksize (:962-1060), split_block (:929-959), the 16-byte header
+ * (:1148-1247) and the MEMCPYED decisions (:1219-1229, :1264-1272).  Everything that
+ * touches the payload -- filters, codecs, the block scheduler and the compaction of
+ * variable-size blocks -- runs as CUDA kernels (dev_*.cuh); there is no CPU codec here.
+ */
+#include "../../include/blosc_b200.h"
+
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "b2_backend.h"
+
+#define MIN_BUFFERSIZE 128        /* blosc.c:73 */
+#define MAX_SPLITS 16             /* blosc.c:76 */
+#define L1_SIZE (32 * 1024)       /* blosc.c:79 */
+
+/* ---- process-global state of the non-ctx API (blosc.c:143-150) ---- */
+static int g_compressor = BLOSC_BLOSCLZ;
+static int g_threads = 1;
+static int g_force_blocksize = 0;
+static int g_initlib = 0;
+static int g_splitmode = BLOSC_FORWARD_COMPAT_SPLIT;
+static pthread_mutex_t g_global_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+/* ---- little-endian header accessors (blosc.c:243-289) ---- */
+static int32_t rd_i32(const uint8_t* p) {
+  return (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+}
+static void wr_i32(uint8_t* p, int32_t v) {
+  uint32_t u = (uint32_t)v;
+  p[0] = (uint8_t)u; p[1] = (uint8_t)(u >> 8); p[2] = (uint8_t)(u >> 16); p[3] = (uint8_t)(u >> 24);
+}
+
+/* ------------------------------------------------------------------------- */
+/* workspace pool: device scratch + one stream per concurrent call            */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  void* p;
+  size_t cap;
+} b2_buf;
+
+typedef struct {
+  int in_use, ready, dev;
+  b2_stream_t stream;
+  b2_buf in, filt, slots, out, csizes, bstarts;
+  int* d_result;        /* [0] cbytes [1] fits [2] decode status */
+  int* h_result;        /* pinned mirror */
+} b2_ws;
+
+#define B2_MAX_WS 16
+static b2_ws g_ws[B2_MAX_WS];
+static pthread_mutex_t g_ws_mutex = PTHREAD_MUTEX_INITIALIZER;
+static int g_backend_state = 0;   /* 0 untried, 1 ok, -1 failed */
+
+static int backend_ready(void) {
+  int st;
+  pthread_mutex_lock(&g_ws_mutex);
+  if (g_backend_state == 0) g_backend_state = b2_backend_init() == 0 ? 1 : -1;
+  st = g_backend_state;
+  pthread_mutex_unlock(&g_ws_mutex);
+  if (st < 0) fprintf(stderr, "blosc_b200: no usable CUDA device -- this library has no CPU codec\n");
+  return st > 0;
+}
+
+static b2_ws* ws_acquire(void) {
+  b2_ws* w = NULL;
+  int i, dev;
+  if (!backend_ready()) return NULL;
+  pthread_mutex_lock(&g_ws_mutex);
+  dev = b2_get_device();
+  for (i = 0; i < B2_MAX_WS; i++)          /* a workspace (stream + scratch) belongs to the device it was made on */
+    if (!g_ws[i].in_use && g_ws[i].ready && g_ws[i].dev == dev) { w = &g_ws[i]; w->in_use = 1; break; }
+  if (!w)
+    for (i = 0; i < B2_MAX_WS; i++)
+      if (!g_ws[i].in_use && !g_ws[i].ready) { w = &g_ws[i]; w->in_use = 1; break; }
+  pthread_mutex_unlock(&g_ws_mutex);
+  if (!w) { fprintf(stderr, "blosc_b200: more than %d concurrent calls\n", B2_MAX_WS); return NULL; }
+  if (!w->ready) {
+    void* p = NULL;
+    if (b2_device_prepare() || b2_stream_create(&w->stream) || b2_dev_alloc(&p, 64)) { w->in_use = 0; return NULL; }
+    w->dev = dev;
+    w->d_result = (int*)p;
+    if (b2_pinned_alloc(&p, 64)) { w->in_use = 0; return NULL; }
+    w->h_result = (int*)p;
+    w->ready = 1;
+  }
+  return w;
+}
+
+static void ws_release(b2_ws* w) {
+  pthread_mutex_lock(&g_ws_mutex);
+  w->in_use = 0;
+  pthread_mutex_unlock(&g_ws_mutex);
+}
+
+static int buf_ensure(b2_buf* b, size_t need) {
+  if (need <= b->cap) return 0;
+  if (b->p) b2_dev_free(b->p);
+  b->p = NULL; b->cap = 0;
+  need = (need + (need >> 3) + 4095) & ~(size_t)4095;    /* slack so slowly growing sizes do not thrash */
+  if (b2_dev_alloc(&b->p, need)) { fprintf(stderr, "blosc_b200: device allocation of %zu bytes failed\n", need); return -1; }
+  b->cap = need;
+  return 0;
+}
+
+static void buf_free(b2_buf* b) { if (b->p) b2_dev_free(b->p); b->p = NULL; b->cap = 0; }
+
+int blosc_free_resources(void) {                              /* blosc.h:411 */
+  int i;
+  pthread_mutex_lock(&g_ws_mutex);
+  for (i = 0; i < B2_MAX_WS; i++) {
+    b2_ws* w = &g_ws[i];
+    if (w->in_use || !w->ready) continue;
+    buf_free(&w->in); buf_free(&w->filt); buf_free(&w->slots); buf_free(&w->out);
+    buf_free(&w->csizes); buf_free(&w->bstarts);
+  }
+  pthread_mutex_unlock(&g_ws_mutex);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* names                                                                      */
+/* ------------------------------------------------------------------------- */
+int blosc_compcode_to_compname(int compcode, const char** compname) {    /* blosc.c:329-374 */
+  static const char* names[6] = {BLOSC_BLOSCLZ_COMPNAME, BLOSC_LZ4_COMPNAME, BLOSC_LZ4HC_COMPNAME,
+                                 BLOSC_SNAPPY_COMPNAME, BLOSC_ZLIB_COMPNAME, BLOSC_ZSTD_COMPNAME};
+  *compname = (compcode >= 0 && compcode < 6) ? names[compcode] : NULL;
+  /* codecs this build can ENCODE; like a reference built without the others */
+  if (compcode == BLOSC_BLOSCLZ || compcode == BLOSC_LZ4) return compcode;
+  return -1;
+}
+
+int blosc_compname_to_compcode(const char* compname) {                    /* blosc.c:377-409 */
+  if (strcmp(compname, BLOSC_BLOSCLZ_COMPNAME) == 0) return BLOSC_BLOSCLZ;
+  if (strcmp(compname, BLOSC_LZ4_COMPNAME) == 0) return BLOSC_LZ4;
+  return -1;
+}
+
+const char* blosc_list_compressors(void) { return BLOSC_BLOSCLZ_COMPNAME "," BLOSC_LZ4_COMPNAME; }   /* blosc.c:2033-2056 */
+const char* blosc_get_version_string(void) { return BLOSC_VERSION_STRING; }
+
+int blosc_get_complib_info(const char* compname, char** complib, char** version) {   /* blosc.c:2063-2124 */
+  int code = -1;
+  const char *lib = NULL, *ver = NULL;
+  if (strcmp(compname, BLOSC_BLOSCLZ_COMPNAME) == 0) { code = BLOSC_BLOSCLZ_LIB; lib = "BloscLZ"; ver = "2.5.1"; }
+  else if (strcmp(compname, BLOSC_LZ4_COMPNAME) == 0 || strcmp(compname, BLOSC_LZ4HC_COMPNAME) == 0) {
+    code = BLOSC_LZ4_LIB; lib = "LZ4"; ver = "1.10.0";
+  }
+  if (code < 0) {
+    if (complib) *complib = NULL;
+    if (version) *version = NULL;
+    return -1;
+  }
+  if (complib) *complib = strdup(lib);
+  if (version) *version = strdup(ver);
+  return code;
+}
+
+static const char* clib_name(int clibcode) {                               /* blosc.c:315-322 */
+  static const char* n[5] = {"BloscLZ", "LZ4", "Snappy", "Zlib", "Zstd"};
+  return (clibcode >= 0 && clibcode < 5) ? n[clibcode] : NULL;
+}
+
+/* ------------------------------------------------------------------------- */
+/* header introspection (host pointers, as in the reference)                   */
+/* ------------------------------------------------------------------------- */
+void blosc_cbuffer_sizes(const void* cbuffer, size_t* nbytes, size_t* cbytes, size_t* blocksize) {   /* blosc.c:2127-2141 */
+  const uint8_t* s = (const uint8_t*)cbuffer;
+  if (s[0] != BLOSC_VERSION_FORMAT) { *nbytes = *blocksize = *cbytes = 0; return; }
+  *nbytes = (size_t)rd_i32(s + 4);
+  *blocksize = (size_t)rd_i32(s + 8);
+  *cbytes = (size_t)rd_i32(s + 12);
+}
+
+int blosc_cbuffer_validate(const void* cbuffer, size_t cbytes, size_t* nbytes) {   /* blosc.c:2143-2150 */
+  size_t hc, hb;
+  if (cbytes < BLOSC_MIN_HEADER_LENGTH) return -1;
+  blosc_cbuffer_sizes(cbuffer, nbytes, &hc, &hb);
+  if (hc != cbytes) return -1;
+  if (*nbytes > BLOSC_MAX_BUFFERSIZE) return -1;
+  return 0;
+}
+
+void blosc_cbuffer_metainfo(const void* cbuffer, size_t* typesize, int* flags) {   /* blosc.c:2153-2168 */
+  const uint8_t* s = (const uint8_t*)cbuffer;
+  if (s[0] != BLOSC_VERSION_FORMAT) { *flags = 0; *typesize = 0; return; }
+  *flags = (int)s[2] & 7;
+  *typesize = (size_t)s[3];
+}
+
+void blosc_cbuffer_versions(const void* cbuffer, int* version, int* versionlz) {   /* blosc.c:2172-2180 */
+  const uint8_t* s = (const uint8_t*)cbuffer;
+  *version = (int)s[0];
+  *versionlz = (int)s[1];
+}
+
+const char* blosc_cbuffer_complib(const void* cbuffer) {                            /* blosc.c:2184-2195 */
+  const uint8_t* s = (const uint8_t*)cbuffer;
+  return clib_name((s[2] & 0xe0) >> 5);
+}
+
+/* ------------------------------------------------------------------------- */
+/* planning                                                                   */
+/* ------------------------------------------------------------------------- */
+static int is_hcr(int compcode) { return compcode == BLOSC_LZ4HC || compcode == BLOSC_ZLIB || compcode == BLOSC_ZSTD; }
+
+static int split_block(int compcode, int typesize, int blocksize) {       /* blosc.c:929-959 */
+  switch (g_splitmode) {
+    case BLOSC_ALWAYS_SPLIT: return 1;
+    case BLOSC_NEVER_SPLIT: return 0;
+    case BLOSC_AUTO_SPLIT:
+      return (compcode == BLOSC_BLOSCLZ || compcode == BLOSC_SNAPPY) && typesize <= MAX_SPLITS &&
+             blocksize / typesize >= MIN_BUFFERSIZE;
+    case BLOSC_FORWARD_COMPAT_SPLIT:
+      return compcode != BLOSC_ZSTD && typesize <= MAX_SPLITS && blocksize / typesize >= MIN_BUFFERSIZE;
+    default:
+      fprintf(stderr, "Split mode %d not supported", g_splitmode);
+      return -1;
+  }
+}
+
+static int32_t compute_blocksize(int compcode, int clevel, int32_t typesize, int32_t nbytes, int32_t forced) {   /* blosc.c:962-1060 */
+  int32_t bs = nbytes;
+  if (nbytes < typesize) return 1;
+  if (forced) {
+    bs = forced;
+    if (bs < MIN_BUFFERSIZE) bs = MIN_BUFFERSIZE;
+    if (bs > (int32_t)BLOSC_MAX_BLOCKSIZE) bs = (int32_t)BLOSC_MAX_BLOCKSIZE;
+  } else if (nbytes >= L1_SIZE) {
+    bs = L1_SIZE;
+    if (is_hcr(compcode)) bs *= 2;
+    switch (clevel) {
+      case 0: bs /= 4; break;
+      case 1: bs /= 2; break;
+      case 2: break;
+      case 3: bs *= 2; break;
+      case 4: case 5: bs *= 4; break;
+      case 6: case 7: case 8: bs *= 8; break;
+      default: bs *= 8; if (is_hcr(compcode)) bs *= 2; break;
+    }
+  }
+  if (clevel > 0 && split_block(compcode, typesize, bs)) {
+    if (bs > (1 << 18)) bs = 1 << 18;
+    bs *= typesize;
+    if (bs < (1 << 16)) bs = 1 << 16;
+    if (bs > 1024 * 1024) bs = 1024 * 1024;
+  }
+  if (bs > nbytes) bs = nbytes;
+  if (bs > typesize) bs = bs / typesize * typesize;
+  return bs;
+}
+
+static int check_threads(int nthreads, int32_t nbytes, int32_t blocksize) {
+  /* do_job takes the pool path (and so validates nthreads, blosc.c:1977-1986) only when
+   * nthreads != 1 and the buffer has more than one block (blosc.c:910) */
+  if (nthreads == 1 || nbytes / blocksize <= 1) return 0;
+  if (nthreads > BLOSC_MAX_THREADS) {
+    fprintf(stderr, "Error.  nthreads cannot be larger than BLOSC_MAX_THREADS (%d)", BLOSC_MAX_THREADS);
+    return -1;
+  }
+  if (nthreads <= 0) { fprintf(stderr, "Error.  nthreads must be a positive integer"); return -1; }
+  return 0;
+}
+
+/* copy between any combination of host / device memory */
+static int copy_any(void* dst, int dst_dev, const void* src, int src_dev, size_t n, b2_stream_t s) {
+  int rc = 0;
+  if (n == 0) return 0;
+  if (!dst_dev && !src_dev) { memcpy(dst, src, n); return 0; }
+  if (dst_dev && src_dev) rc = b2_copy_d2d(dst, src, n, s);
+  else if (dst_dev) rc = b2_copy_h2d(dst, src, n, s);
+  else rc = b2_copy_d2h(dst, src, n, s);
+  if (rc == 0) rc = b2_stream_sync(s);
+  return rc;
+}
+
+static void make_header(uint8_t* h, int versionlz, int flags, int typesize, int32_t nbytes, int32_t blocksize,
+                        int32_t cbytes) {                                  /* blosc.c:1154-1215,1275 */
+  h[0] = BLOSC_VERSION_FORMAT; h[1] = (uint8_t)versionlz; h[2] = (uint8_t)flags; h[3] = (uint8_t)typesize;
+  wr_i32(h + 4, nbytes); wr_i32(h + 8, blocksize); wr_i32(h + 12, cbytes);
+}
+
+/* header + raw payload (blosc.c:825-830) */
+static int emit_memcpyed(const uint8_t* hdr, const void* src, int src_dev, void* dest, int dest_dev, int32_t nbytes) {
+  b2_ws* w = NULL;
+  int rc = 0;
+  if (src_dev || dest_dev) { w = ws_acquire(); if (!w) return -1; }
+  rc = copy_any(dest, dest_dev, hdr, 0, 16, w ? w->stream : NULL);
+  if (!rc) rc = copy_any((uint8_t*)dest + 16, dest_dev, src, src_dev, (size_t)nbytes, w ? w->stream : NULL);
+  if (w) ws_release(w);
+  return rc ? -1 : nbytes + 16;
+}
+
+/* ------------------------------------------------------------------------- */
+/* compression                                                                */
+/* ------------------------------------------------------------------------- */
+int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src, void* dest,
+                       size_t destsize, const char* compressor, size_t blocksize, int numinternalthreads) {
+  const int compcode = blosc_compname_to_compcode(compressor);
+  int32_t ts, nb, bs, nblocks, leftover, dsz;
+  int flags = 0, compformat, dont_split, src_dev, dest_dev, dofilter, fmode = 0, nsplits, result = -1;
+  uint8_t hdr[16];
+  b2_ws* w;
+  const uint8_t* d_src;
+  const uint8_t* d_codec_in;
+  uint8_t* d_dest;
+
+  /* initialize_context_compression, blosc.c:1062-1145 */
+  if (nbytes > BLOSC_MAX_BUFFERSIZE) return 0;
+  if (destsize < BLOSC_MAX_OVERHEAD) return 0;
+  if (destsize - BLOSC_MAX_OVERHEAD > nbytes) destsize = nbytes + BLOSC_MAX_OVERHEAD;
+  if (clevel < 0 || clevel > 9) return -10;
+  if (doshuffle != 0 && doshuffle != 1 && doshuffle != 2) return -10;
+  if (typesize == 0) return -10;
+  if (typesize > BLOSC_MAX_TYPESIZE) typesize = 1;
+  ts = (int32_t)typesize; nb = (int32_t)nbytes; dsz = (int32_t)destsize;
+  bs = compute_blocksize(compcode, clevel, ts, nb, (int32_t)blocksize);
+  nblocks = nb / bs; leftover = nb % bs;
+  if (leftover > 0) nblocks++;
+
+  /* write_compression_header, blosc.c:1148-1247 */
+  if (compcode == BLOSC_BLOSCLZ) compformat = BLOSC_BLOSCLZ_FORMAT;
+  else if (compcode == BLOSC_LZ4) compformat = BLOSC_LZ4_FORMAT;
+  else {
+    fprintf(stderr, "Blosc has not been compiled with '%s' ", compressor ? compressor : "(null)");
+    fprintf(stderr, "compression support.  Please use one having it.");
+    return -5;
+  }
+  if (clevel == 0) flags |= BLOSC_MEMCPYED;
+  if (nb < MIN_BUFFERSIZE) flags |= BLOSC_MEMCPYED;
+  if (doshuffle == BLOSC_SHUFFLE) flags |= BLOSC_DOSHUFFLE;
+  if (doshuffle == BLOSC_BITSHUFFLE) flags |= BLOSC_DOBITSHUFFLE;
+  dont_split = !split_block(compcode, ts, bs);
+  flags |= dont_split << 4;
+  flags |= compformat << 5;
+
+  src_dev = (nb > 0) ? b2_ptr_is_device(src) : 0;
+  dest_dev = b2_ptr_is_device(dest);
+
+  /* blosc_compress_context, blosc.c:1250-1279 */
+  if ((flags & BLOSC_MEMCPYED) && nb + BLOSC_MAX_OVERHEAD > dsz) return 0;
+  if (check_threads(numinternalthreads, nb, bs) < 0) return -1;
+  if (flags & BLOSC_MEMCPYED) {
+    make_header(hdr, 1, flags, ts, nb, bs, nb + 16);
+    return emit_memcpyed(hdr, src, src_dev, dest, dest_dev, nb);
+  }
+
+  w = ws_acquire();
+  if (!w) return -1;
+  do {
+    FilterArgs fa;
+    EncodeArgs ea;
+    ScanArgs sa;
+    CompactArgs ca;
+    const int32_t nfull = nb / bs;
+    /* stage the input on the device if it lives in host memory */
+    if (src_dev) d_src = (const uint8_t*)src;
+    else {
+      if (buf_ensure(&w->in, (size_t)nb + 64)) break;
+      if (b2_copy_h2d(w->in.p, src, (size_t)nb, w->stream)) break;
+      d_src = (const uint8_t*)w->in.p;
+    }
+    /* filter (blosc.c:607-622): byte shuffle needs typesize > 1; bitshuffle applies per block when bsize >= typesize */
+    dofilter = ((flags & BLOSC_DOSHUFFLE) && ts > 1) || (flags & BLOSC_DOBITSHUFFLE);
+    if ((flags & BLOSC_DOSHUFFLE) && ts > 1) fmode = FILT_SHUFFLE; else fmode = FILT_BITSHUFFLE;
+    d_codec_in = d_src;
+    if (dofilter) {
+      if (buf_ensure(&w->filt, (size_t)nb + 64)) break;
+      fa.src = d_src; fa.dst = (uint8_t*)w->filt.p; fa.nbytes = nb; fa.blocksize = bs; fa.typesize = ts; fa.mode = fmode;
+      if (b2_launch_filter(&fa, w->stream)) break;
+      d_codec_in = (const uint8_t*)w->filt.p;
+    }
+    /* one LZ stream per split (blosc.c:628-634) */
+    nsplits = dont_split ? 1 : ts;
+    memset(&ea, 0, sizeof ea);
+    ea.map.nbytes = nb; ea.map.blocksize = bs; ea.map.nsplits = nsplits; ea.map.first_block = 0;
+    ea.map.nfull = nfull; ea.map.leftover = leftover; ea.map.nstreams = nfull * nsplits + (leftover ? 1 : 0);
+    if (buf_ensure(&w->slots, (size_t)nb + 64)) break;
+    if (buf_ensure(&w->csizes, (size_t)ea.map.nstreams * 4 + 64)) break;
+    if (buf_ensure(&w->bstarts, (size_t)nblocks * 4 + 64)) break;
+    ea.in = d_codec_in; ea.slots = (uint8_t*)w->slots.p; ea.csizes = (int*)w->csizes.p;
+    ea.codec = compcode == BLOSC_LZ4 ? B2_CODEC_LZ4 : B2_CODEC_BLOSCLZ;
+    ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
+    ea.split_flag = !dont_split;
+    ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
+    if (b2_launch_encode(&ea, w->stream)) break;
+    sa.csizes = ea.csizes; sa.bstarts = (int*)w->bstarts.p; sa.result = w->d_result;
+    sa.nsplits = nsplits; sa.nfull = nfull; sa.has_leftover = leftover > 0; sa.destsize = dsz;
+    if (b2_launch_scan(&sa, w->stream)) break;
+    if (dest_dev) d_dest = (uint8_t*)dest;
+    else { if (buf_ensure(&w->out, (size_t)dsz + 64)) break; d_dest = (uint8_t*)w->out.p; }
+    ca.map = ea.map; ca.in = d_codec_in; ca.slots = ea.slots; ca.csizes = ea.csizes; ca.bstarts = sa.bstarts;
+    ca.result = w->d_result; ca.dest = d_dest;
+    ca.hdr0 = (uint32_t)BLOSC_VERSION_FORMAT | (1u << 8) | ((uint32_t)flags << 16) | ((uint32_t)ts << 24);
+    ca.nbytes32 = nb; ca.nblocks = nblocks;
+    if (b2_launch_compact(&ca, w->stream)) break;
+    if (b2_copy_d2h(w->h_result, w->d_result, 8, w->stream)) break;
+    if (b2_stream_sync(w->stream)) break;
+    if (w->h_result[1]) {                                                 /* fits */
+      const int32_t cbytes = w->h_result[0];
+      if (!dest_dev) {
+        if (b2_copy_d2h(dest, d_dest, (size_t)cbytes, w->stream)) break;
+        if (b2_stream_sync(w->stream)) break;
+      }
+      result = cbytes;
+    } else if (nb + BLOSC_MAX_OVERHEAD <= dsz) {                          /* blosc.c:1264-1272 */
+      result = -2;   /* marker: redo as MEMCPYED after releasing the workspace */
+    } else {
+      make_header(hdr, 1, flags, ts, nb, bs, 0);                          /* blosc.c:1275 with ntbytes == 0 */
+      if (copy_any(dest, dest_dev, hdr, 0, 16, w->stream)) break;
+      result = 0;
+    }
+  } while (0);
+  ws_release(w);
+  if (result == -2) {
+    flags |= BLOSC_MEMCPYED;
+    make_header(hdr, 1, flags, ts, nb, bs, nb + 16);
+    return emit_memcpyed(hdr, src, src_dev, dest, dest_dev, nb);
+  }
+  return result;
+}
+
+/* ------------------------------------------------------------------------- */
+/* decompression                                                              */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int version, versionlz, flags, typesize;
+  int32_t nbytes, blocksize, cbytes, nblocks, leftover;
+} b2_hdr;
+
+static void parse_header(const uint8_t* h, b2_hdr* o) {                    /* blosc.c:1453-1461 */
+  o->version = h[0]; o->versionlz = h[1]; o->flags = h[2]; o->typesize = h[3];
+  o->nbytes = rd_i32(h + 4); o->blocksize = rd_i32(h + 8); o->cbytes = rd_i32(h + 12);
+  o->nblocks = 0; o->leftover = 0;
+}
+
+static int codec_from_header(const b2_hdr* h, int* codec) {                /* blosc.c:525-574 */
+  const int fmt = (h->flags & 0xe0) >> 5;
+  if (fmt == BLOSC_BLOSCLZ_FORMAT) { if (h->versionlz != BLOSC_BLOSCLZ_VERSION_FORMAT) return -9; *codec = B2_CODEC_BLOSCLZ; return 0; }
+  if (fmt == BLOSC_LZ4_FORMAT) { if (h->versionlz != BLOSC_LZ4_VERSION_FORMAT) return -9; *codec = B2_CODEC_LZ4; return 0; }
+  return -5;
+}
+
+/* Decode blocks [first, first+count) of a chunk that is already on the device into `d_out`
+ * (device), which represents buffer offsets [first*blocksize, ...).  Shared by decompress and getitem. */
+static int decode_blocks(b2_ws* w, const b2_hdr* h, int codec, const uint8_t* d_chunk, int first, int count,
+                         uint8_t* d_out) {
+  DecodeArgs da;
+  FilterArgs fa;
+  const int ts = h->typesize, bs = h->blocksize;
+  const int dont_split = (h->flags & 0x10) >> 4;
+  const int doshuffle = (h->flags & BLOSC_DOSHUFFLE) && ts > 1;
+  const int dobitshuffle = !doshuffle && (h->flags & BLOSC_DOBITSHUFFLE);
+  const int has_left = h->leftover > 0 && first + count == h->nblocks;
+  const int nfull = count - has_left;
+  const long long span = (long long)nfull * bs + (has_left ? h->leftover : 0);
+  uint8_t* d_codec_out = d_out;
+  memset(&da, 0, sizeof da);
+  /* blosc.c:749-757: split only if typesize <= 16 and >= 128 elements per block */
+  da.map.nsplits = (!dont_split && ts <= MAX_SPLITS && bs / ts >= MIN_BUFFERSIZE) ? ts : 1;
+  da.map.nbytes = h->nbytes; da.map.blocksize = bs; da.map.first_block = first; da.map.nfull = nfull;
+  da.map.leftover = has_left ? h->leftover : 0;
+  da.map.nstreams = nfull * da.map.nsplits + (has_left ? 1 : 0);
+  if (doshuffle || dobitshuffle) {
+    if (buf_ensure(&w->filt, (size_t)span + 64)) return -1;
+    d_codec_out = (uint8_t*)w->filt.p;
+  }
+  if (b2_memset_dev(w->d_result + 2, 0, 4, w->stream)) return -1;
+  da.chunk = d_chunk; da.cbytes = h->cbytes; da.out = d_codec_out; da.out_shift = (long long)first * bs;
+  da.codec = codec; da.status = w->d_result + 2;
+  if (b2_launch_decode(&da, w->stream)) return -1;
+  if (doshuffle || dobitshuffle) {
+    fa.src = d_codec_out; fa.dst = d_out; fa.nbytes = span; fa.blocksize = bs; fa.typesize = ts;
+    fa.mode = doshuffle ? FILT_UNSHUFFLE : FILT_BITUNSHUFFLE;
+    if (b2_launch_filter(&fa, w->stream)) return -1;
+  }
+  if (b2_copy_d2h(w->h_result + 2, w->d_result + 2, 4, w->stream)) return -1;
+  if (b2_stream_sync(w->stream)) return -1;
+  return w->h_result[2] < 0 ? w->h_result[2] : 0;
+}
+
+int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numinternalthreads) {
+  uint8_t hb[16];
+  b2_hdr h;
+  int src_dev, dest_dev, codec = 0, rc, result = -1;
+  b2_ws* w;
+
+  src_dev = b2_ptr_is_device(src);
+  if (src_dev) {
+    w = ws_acquire();
+    if (!w) return -1;
+    rc = copy_any(hb, 0, src, 1, 16, w->stream);
+    ws_release(w);
+    if (rc) return -1;
+  } else memcpy(hb, src, 16);
+  parse_header(hb, &h);
+
+  /* blosc_run_decompression_with_context, blosc.c:1463-1508 */
+  if (h.nbytes == 0) return 0;
+  if (h.blocksize <= 0 || (size_t)h.blocksize > destsize || (size_t)h.blocksize > BLOSC_MAX_BLOCKSIZE || h.typesize <= 0)
+    return -1;
+  if (h.version != BLOSC_VERSION_FORMAT) return -1;
+  if (h.flags & 0x08) return -1;
+  h.nblocks = h.nbytes / h.blocksize; h.leftover = h.nbytes % h.blocksize;
+  if (h.leftover > 0) h.nblocks++;
+  if (h.nbytes > (int32_t)destsize) return -1;
+  dest_dev = b2_ptr_is_device(dest);
+  if (h.flags & BLOSC_MEMCPYED) {
+    if (h.nbytes + BLOSC_MAX_OVERHEAD != h.cbytes) return -1;
+  } else {
+    rc = codec_from_header(&h, &codec);
+    if (rc) return rc;
+    if (h.nblocks > (h.cbytes - 16) / 4) return -1;
+  }
+  if (check_threads(numinternalthreads, h.nbytes, h.blocksize) < 0) return -1;
+
+  if (h.flags & BLOSC_MEMCPYED) {                                          /* blosc.c:843-848 */
+    w = NULL;
+    if (src_dev || dest_dev) { w = ws_acquire(); if (!w) return -1; }
+    rc = copy_any(dest, dest_dev, (const uint8_t*)src + 16, src_dev, (size_t)h.nbytes, w ? w->stream : NULL);
+    if (w) ws_release(w);
+    return rc ? -1 : h.nbytes;
+  }
+
+  w = ws_acquire();
+  if (!w) return -1;
+  do {
+    const uint8_t* d_chunk;
+    uint8_t* d_out;
+    if (src_dev) d_chunk = (const uint8_t*)src;
+    else {
+      if (buf_ensure(&w->in, (size_t)h.cbytes + 64)) break;
+      if (b2_copy_h2d(w->in.p, src, (size_t)h.cbytes, w->stream)) break;
+      d_chunk = (const uint8_t*)w->in.p;
+    }
+    if (dest_dev) d_out = (uint8_t*)dest;
+    else { if (buf_ensure(&w->out, (size_t)h.nbytes + 64)) break; d_out = (uint8_t*)w->out.p; }
+    rc = decode_blocks(w, &h, codec, d_chunk, 0, h.nblocks, d_out);
+    if (rc < 0) { result = -1; break; }                                    /* blosc.c:1511-1514 */
+    if (!dest_dev) {
+      if (b2_copy_d2h(dest, d_out, (size_t)h.nbytes, w->stream)) break;
+      if (b2_stream_sync(w->stream)) break;
+    }
+    result = h.nbytes;
+  } while (0);
+  ws_release(w);
+  return result;
+}
+
+int blosc_getitem(const void* src, int start, int nitems, void* dest) {    /* blosc.c:1574-1703 */
+  uint8_t hb[16];
+  b2_hdr h;
+  int src_dev, dest_dev, codec = 0, rc, result = -1;
+  const int stop = start + nitems;
+  b2_ws* w;
+  long long b_lo, b_hi, first, last;
+
+  src_dev = b2_ptr_is_device(src);
+  if (src_dev) {
+    w = ws_acquire();
+    if (!w) return -1;
+    rc = copy_any(hb, 0, src, 1, 16, w->stream);
+    ws_release(w);
+    if (rc) return -1;
+  } else memcpy(hb, src, 16);
+  parse_header(hb, &h);
+  if (h.version != BLOSC_VERSION_FORMAT) return -9;
+  if (h.blocksize <= 0 || h.blocksize > h.nbytes || (size_t)h.blocksize > BLOSC_MAX_BLOCKSIZE || h.typesize <= 0)
+    return -1;
+  h.nblocks = h.nbytes / h.blocksize; h.leftover = h.nbytes % h.blocksize;
+  if (h.leftover > 0) h.nblocks++;
+  if (h.flags & BLOSC_MEMCPYED) {
+    if (h.nbytes + BLOSC_MAX_OVERHEAD != h.cbytes) return -1;
+  } else {
+    rc = codec_from_header(&h, &codec);
+    if (rc) return rc;
+    if (h.nblocks >= (h.cbytes - 16) / 4) return -1;                       /* :1630 */
+  }
+  if (start < 0 || (long long)start * h.typesize > h.nbytes) { fprintf(stderr, "`start` out of bounds"); return -1; }
+  if (stop < 0 || (long long)stop * h.typesize > h.nbytes) { fprintf(stderr, "`start`+`nitems` out of bounds"); return -1; }
+  b_lo = (long long)start * h.typesize; b_hi = (long long)stop * h.typesize;
+  if (b_hi <= b_lo) return 0;                                              /* no block overlaps: loop copies nothing */
+  dest_dev = b2_ptr_is_device(dest);
+
+  if (h.flags & BLOSC_MEMCPYED) {                                          /* :1678-1683 */
+    w = NULL;
+    if (src_dev || dest_dev) { w = ws_acquire(); if (!w) return -1; }
+    rc = copy_any(dest, dest_dev, (const uint8_t*)src + 16 + b_lo, src_dev, (size_t)(b_hi - b_lo), w ? w->stream : NULL);
+    if (w) ws_release(w);
+    return rc ? -1 : (int)(b_hi - b_lo);
+  }
+
+  first = b_lo / h.blocksize; last = (b_hi - 1) / h.blocksize;             /* only overlapping blocks are decoded, :1666 */
+  w = ws_acquire();
+  if (!w) return -1;
+  do {
+    const uint8_t* d_chunk;
+    const int count = (int)(last - first + 1);
+    if (src_dev) d_chunk = (const uint8_t*)src;
+    else {
+      if (buf_ensure(&w->in, (size_t)h.cbytes + 64)) break;
+      if (b2_copy_h2d(w->in.p, src, (size_t)h.cbytes, w->stream)) break;
+      d_chunk = (const uint8_t*)w->in.p;
+    }
+    if (buf_ensure(&w->out, (size_t)count * (size_t)h.blocksize + 64)) break;
+    rc = decode_blocks(w, &h, codec, d_chunk, (int)first, count, (uint8_t*)w->out.p);
+    if (rc < 0) { result = rc; break; }                                    /* :1689-1692 returns blosc_d's code */
+    if (copy_any(dest, dest_dev, (const uint8_t*)w->out.p + (b_lo - first * h.blocksize), 1, (size_t)(b_hi - b_lo), w->stream)) break;
+    result = (int)(b_hi - b_lo);
+  } while (0);
+  ws_release(w);
+  return result;
+}
+
+/* ------------------------------------------------------------------------- */
+/* global-state front end                                                     */
+/* ------------------------------------------------------------------------- */
+void blosc_init(void) { g_initlib = 1; }                                    /* blosc.c:2223-2247 (no pool to create) */
+void blosc_destroy(void) { if (g_initlib) { g_initlib = 0; blosc_free_resources(); } }   /* blosc.c:2249-2260 */
+int blosc_get_nthreads(void) { return g_threads; }
+int blosc_set_nthreads(int n) { int old = g_threads; if (!g_initlib) blosc_init(); g_threads = n; return old; }   /* blosc.c:1958-1975 */
+const char* blosc_get_compressor(void) { const char* n; blosc_compcode_to_compname(g_compressor, &n); return n; }
+int blosc_set_compressor(const char* compname) {                            /* blosc.c:2013-2023 */
+  int code = blosc_compname_to_compcode(compname);
+  g_compressor = code;
+  if (!g_initlib) blosc_init();
+  return code;
+}
+int blosc_get_blocksize(void) { return g_force_blocksize; }
+void blosc_set_blocksize(size_t size) { g_force_blocksize = (int32_t)size; }
+void blosc_set_splitmode(int mode) { g_splitmode = mode; }
+
+int blosc_compress(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src, void* dest,
+                   size_t destsize) {                                      /* blosc.c:1311-1433 */
+  const char* envvar;
+  const char* compname;
+  int result, nolock;
+  if (!g_initlib) blosc_init();
+  if ((envvar = getenv("BLOSC_CLEVEL")) != NULL) { long v = strtol(envvar, NULL, 10); if (v != EINVAL && v >= 0) clevel = (int)v; }
+  if ((envvar = getenv("BLOSC_SHUFFLE")) != NULL) {
+    if (strcmp(envvar, "NOSHUFFLE") == 0) doshuffle = BLOSC_NOSHUFFLE;
+    if (strcmp(envvar, "SHUFFLE") == 0) doshuffle = BLOSC_SHUFFLE;
+    if (strcmp(envvar, "BITSHUFFLE") == 0) doshuffle = BLOSC_BITSHUFFLE;
+  }
+  if ((envvar = getenv("BLOSC_TYPESIZE")) != NULL) { long v = strtol(envvar, NULL, 10); if (v != EINVAL && v > 0) typesize = (size_t)(int)v; }
+  if ((envvar = getenv("BLOSC_COMPRESSOR")) != NULL) { result = blosc_set_compressor(envvar); if (result < 0) return result; }
+  if ((envvar = getenv("BLOSC_BLOCKSIZE")) != NULL) { long v = strtol(envvar, NULL, 10); if (v != EINVAL && v > 0) blosc_set_blocksize((size_t)v); }
+  if ((envvar = getenv("BLOSC_NTHREADS")) != NULL) { long v = strtol(envvar, NULL, 10); if (v != EINVAL && v > 0) { result = blosc_set_nthreads((int)v); if (result < 0) return result; } }
+  if ((envvar = getenv("BLOSC_SPLITMODE")) != NULL) {
+    if (strcmp(envvar, "FORWARD_COMPAT") == 0) blosc_set_splitmode(BLOSC_FORWARD_COMPAT_SPLIT);
+    else if (strcmp(envvar, "AUTO") == 0) blosc_set_splitmode(BLOSC_AUTO_SPLIT);
+    else if (strcmp(envvar, "ALWAYS") == 0) blosc_set_splitmode(BLOSC_ALWAYS_SPLIT);
+    else if (strcmp(envvar, "NEVER") == 0) blosc_set_splitmode(BLOSC_NEVER_SPLIT);
+    else { fprintf(stderr, "BLOSC_SPLITMODE environment variable '%s' not recognized\n", envvar); return -1; }
+  }
+  nolock = getenv("BLOSC_NOLOCK") != NULL;
+  blosc_compcode_to_compname(g_compressor, &compname);
+  if (compname == NULL) compname = "(null)";
+  /* the global path serialises callers on one mutex (blosc.c:1410); BLOSC_NOLOCK skips it (:1400-1408) */
+  if (!nolock) pthread_mutex_lock(&g_global_mutex);
+  result = blosc_compress_ctx(clevel, doshuffle, typesize, nbytes, src, dest, destsize, compname,
+                              (size_t)g_force_blocksize, g_threads);
+  if (!nolock) pthread_mutex_unlock(&g_global_mutex);
+  return result;
+}
+
+int blosc_decompress(const void* src, void* dest, size_t destsize) {        /* blosc.c:1537-1572 */
+  const char* envvar;
+  int result, nolock;
+  if (!g_initlib) blosc_init();
+  if ((envvar = getenv("BLOSC_NTHREADS")) != NULL) { long v = strtol(envvar, NULL, 10); if (v != EINVAL && v > 0) { result = blosc_set_nthreads((int)v); if (result < 0) return result; } }
+  nolock = getenv("BLOSC_NOLOCK") != NULL;
+  if (!nolock) pthread_mutex_lock(&g_global_mutex);
+  result = blosc_decompress_ctx(src, dest, destsize, g_threads);
+  if (!nolock) pthread_mutex_unlock(&g_global_mutex);
+  return result;
+}
+
+/* ------------------------------------------------------------------------- */
+/* B200 extensions                                                            */
+/* ------------------------------------------------------------------------- */
+int blosc_b200_filter(int mode, size_t typesize, size_t blocksize, const void* src, void* dest) {
+  b2_ws* w;
+  FilterArgs fa;
+  int src_dev, dest_dev, rc = -1;
+  if (mode < 0 || mode > 3 || typesize == 0 || blocksize > (size_t)INT_MAX) return -1;
+  if (blocksize == 0) return 0;
+  src_dev = b2_ptr_is_device(src); dest_dev = b2_ptr_is_device(dest);
+  w = ws_acquire();
+  if (!w) return -1;
+  do {
+    const uint8_t* d_src = (const uint8_t*)src;
+    uint8_t* d_dst = (uint8_t*)dest;
+    if (!src_dev) {
+      if (buf_ensure(&w->in, blocksize + 64)) break;
+      if (b2_copy_h2d(w->in.p, src, blocksize, w->stream)) break;
+      d_src = (const uint8_t*)w->in.p;
+    }
+    if (!dest_dev) { if (buf_ensure(&w->out, blocksize + 64)) break; d_dst = (uint8_t*)w->out.p; }
+    fa.src = d_src; fa.dst = d_dst; fa.nbytes = (long long)blocksize; fa.blocksize = (int)blocksize;
+    fa.typesize = (int)typesize; fa.mode = mode;
+    if (b2_launch_filter(&fa, w->stream)) break;
+    if (!dest_dev && b2_copy_d2h(dest, d_dst, blocksize, w->stream)) break;
+    if (b2_stream_sync(w->stream)) break;
+    rc = 0;
+  } while (0);
+  ws_release(w);
+  return rc;
+}
+
+int blosc_b200_set_device(int dev) { return backend_ready() ? b2_set_device(dev) : -1; }
+void blosc_b200_set_profiling(int on) { b2_prof_enable(on); }
+void blosc_b200_prof_reset(void) { b2_prof_reset(); }
+int blosc_b200_prof_get(int kind, double* ms_total, long long* launches) { return b2_prof_get(kind, ms_total, launches); }
+long long blosc_b200_launch_count(void) { return b2_launch_count(); }

@@ -1,0 +1,282 @@
+/*
+ * dev_blosclz.cuh -- BloscLZ codec, one warp per stream, sm_100a.
+ *
+ * Encoder: bit-exact replay of blosclz_compress (reference blosc/blosclz.c:421-613)
+ * including its entropy probe get_cratio (:318-418).  BloscLZ visits EVERY position
+ * (a miss costs one literal and advances by one), so a round examines the 32
+ * consecutive positions ip..ip+31: each lane hashes its position, resolves the table
+ * state it would observe (the table from earlier rounds, overridden by the nearest
+ * lower lane with the same hash), and -- because the reference accepts a candidate
+ * only if the match is long enough (len >= minlen, and > 5 for far matches,
+ * blosclz.c:535) -- compares up to 12 bytes to take exactly that decision.  The first
+ * accepting lane f yields f literals + one match; positions up to f are committed to
+ * the table.  The result is byte-identical to the serial encoder.
+ *
+ * Decoder: blosclz_decompress (blosclz.c:679-789) with warp-wide copies.
+ */
+#pragma once
+#include "dev_common.cuh"
+
+#define BLZ_MAX_COPY 32
+#define BLZ_MAX_DISTANCE 8191                      /* blosclz.c:43 */
+#define BLZ_MAX_FARDISTANCE (65535 + 8191 - 1)     /* blosclz.c:44 */
+#define BLZ_PROBE_TABLE_BYTES 8192                 /* 2^12 x u16, blosclz.c:321-322 */
+
+DEV u32 blz_hash(u32 seq, u32 hashlog) { return (seq * 2654435761u) >> (32u - hashlog); }   /* blosclz.c:58-60 */
+
+/* min(p+1, bound) with p the first position >= start where b[p] != b[p-dist]
+ * (what get_run_or_match returns, blosclz.c:117-243). */
+DEV int blz_match_end_warp(const u8* __restrict__ b, int start, int dist, int bound) {
+  const int p = start + warp_count_match(b, start, start - dist, bound);
+  return p < bound ? p + 1 : bound;
+}
+
+/* One search round shared by the probe and the encoder.  Examines positions
+ * ip .. ip+31 (those < ip_limit).  Returns the first accepting lane (32 if none),
+ * the number of valid lanes in *nvalid, and for the accepting lane its candidate and
+ * its capped match length (4..12) in *cand_f / *m_f.  Commits table entries. */
+template <typename TabT, bool FARRULE>
+DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, TabT* tab, u32 hashlog,
+                         int ipshift, int minlen, int* nvalid, int* cand_f, int* m_f) {
+  const int lane = lane_id();
+  const int pos = ip + lane;
+  const bool valid = pos < ip_limit;
+  u32 seq = 0, h = 0x80000000u | (u32)lane;
+  if (valid) { seq = ld_u32(b + pos); h = blz_hash(seq, hashlog); }
+  const unsigned vmask = __ballot_sync(FULLMASK, valid);
+  const unsigned peers = __match_any_sync(FULLMASK, h);
+  const unsigned lower = peers & ((1u << lane) - 1u);
+  int cand = 0, m = 0;
+  bool acc = false;
+  if (valid) {
+    cand = lower ? ip + (31 - __clz((int)lower)) : (int)tab[h];
+    const u32 dist = (u32)(pos - cand);                                    /* blosclz.c:501 */
+    if (dist != 0 && dist < BLZ_MAX_FARDISTANCE && ld_u32(b + cand) == seq) {   /* :506,:512 */
+      const u32 x1 = ld_u32(b + pos + 4) ^ ld_u32(b + cand + 4);
+      if (x1) m = 4 + eq_bytes32(x1);
+      else m = 8 + eq_bytes32(ld_u32(b + pos + 8) ^ ld_u32(b + cand + 8));
+      /* m equal bytes (capped at 12) => match end = pos+m+1 => len = m+1-ipshift (:527-532) */
+      const int len = m + 1 - ipshift;
+      const bool far = FARRULE && (dist - 1u >= BLZ_MAX_DISTANCE);
+      acc = m >= 12 || (len >= minlen && !(len <= 5 && far));               /* :535 */
+    }
+  }
+  const unsigned found = __ballot_sync(FULLMASK, acc);
+  const int nv = __popc(vmask);
+  const int f = found ? __ffs((int)found) - 1 : 32;
+  const int last = f < nv - 1 ? f : nv - 1;
+  if (valid && lane <= last) {
+    const unsigned le = last >= 31 ? FULLMASK : ((1u << (last + 1)) - 1u);
+    if ((((peers & le) >> lane) >> 1) == 0) tab[h] = (TabT)pos;           /* :504, last writer per hash */
+  }
+  __syncwarp();
+  *nvalid = nv;
+  if (found) {
+    *cand_f = __shfl_sync(FULLMASK, cand, f);
+    *m_f = __shfl_sync(FULLMASK, m, f);
+  }
+  return f;
+}
+
+/* get_cratio (blosclz.c:318-418) on the probe window b[0..maxlen).  `tabmem` is
+ * BLZ_PROBE_TABLE_BYTES of warp-private shared memory. */
+DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
+  const int lane = lane_id();
+  u16* tab = (u16*)tabmem;
+  for (int i = lane; i < BLZ_PROBE_TABLE_BYTES / 4; i += 32) ((u32*)tabmem)[i] = 0;
+  __syncwarp();
+  const int limit = maxlen > 4096 ? 4096 : maxlen;
+  const int ip_bound = limit - 1, ip_limit = limit - 12;
+  int ip = 0, oc = 5, copy = 4;
+  while (ip < ip_limit) {
+    int nvalid, cand, m;
+    const int f = blz_search_round<u16, false>(b, ip, ip_limit, tab, 12, 3, 3, &nvalid, &cand, &m);
+    const int nlit = f < 32 ? f : nvalid;
+    oc += nlit + ((copy + nlit) >> 5);                       /* LITERAL2, :258-266 */
+    copy = (copy + nlit) & 31;
+    ip += nlit;
+    if (f == 32) continue;
+    const int anchor = ip, dist = anchor - cand;
+    const int e = m < 12 ? anchor + m + 1 : blz_match_end_warp(b, anchor + 12, dist, ip_bound);
+    ip = e - 3;
+    const int len = ip - anchor;
+    if (!copy) oc--;                                         /* :386-390 */
+    copy = 0;
+    if (len >= 7) oc += (len - 7) / 255 + 1;
+    oc += (dist - 1 < BLZ_MAX_DISTANCE) ? 2 : 4;
+    if (lane == 0) tab[blz_hash(ld_u32(b + ip), 12)] = (u16)ip;   /* :407-411 */
+    __syncwarp();
+    ip += 2;
+    oc++;
+  }
+  return (double)ip / (double)oc;
+}
+
+/* blosclz_compress for one stream.  Returns the compressed size or 0 (not
+ * compressible / does not fit in maxout).  `tabmem`: (4 << hashlog) bytes, at least
+ * BLZ_PROBE_TABLE_BYTES, warp-private shared memory. */
+DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int length, u8* __restrict__ out,
+                        const int maxout, const int split_block, void* tabmem) {
+  const int lane = lane_id();
+  const int maxlen = length / 4, shift = length - maxlen;
+  const double cratio = blz_probe_warp(b + shift, maxlen, tabmem);          /* :425-430 */
+  double thr;
+  switch (clevel) {                                                          /* :432 */
+    case 0: thr = 0; break;
+    case 1: thr = 2; break;
+    case 2: thr = 1.5; break;
+    case 7: thr = 1.15; break;
+    case 8: thr = 1.1; break;
+    case 9: thr = 1.0; break;
+    default: thr = 1.2; break;
+  }
+  if (cratio < thr) return 0;
+  int ipshift = 4, minlen = 4;
+  if (!split_block || cratio < 4) { ipshift = 3; minlen = 3; }               /* :445-457 */
+  const u32 hashlog = clevel == 1 ? 12u : (clevel == 2 ? 13u : 14u);         /* :459-461 */
+  if (length < 16 || maxout < 66) return 0;                                  /* :473-475 */
+
+  u32* tab = (u32*)tabmem;
+  __syncwarp();
+  for (int i = lane; i < (1 << hashlog); i += 32) tab[i] = 0;
+  __syncwarp();
+
+  const int ip_bound = length - 1, ip_limit = length - 12, op_limit = maxout;
+  int ip = 4, op = 5, copy = 4;
+  if (lane == 0) { out[0] = BLZ_MAX_COPY - 1; out[1] = b[0]; out[2] = b[1]; out[3] = b[2]; out[4] = b[3]; }   /* :481-487 */
+
+  while (ip < ip_limit) {
+    int nvalid, cand, m;
+    const int f = blz_search_round<u32, true>(b, ip, ip_limit, tab, hashlog, ipshift, minlen, &nvalid, &cand, &m);
+    const int nlit = f < 32 ? f : nvalid;
+    if (nlit > 0) {                                                          /* LITERAL x nlit, :246-256 */
+      if (op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2 > op_limit) return 0;
+      if (lane < nlit) {
+        const int o = op + lane + ((copy + lane) >> 5);
+        out[o] = b[ip + lane];
+        if (((copy + lane + 1) & 31) == 0) out[o + 1] = BLZ_MAX_COPY - 1;
+      }
+      op += nlit + ((copy + nlit) >> 5);
+      copy = (copy + nlit) & 31;
+      ip += nlit;
+      __syncwarp();            /* a lane may have written the control byte that lane 0 patches below */
+    }
+    if (f == 32) continue;
+
+    const int anchor = ip;
+    u32 distance = (u32)(anchor - cand) - 1u;                                /* biased, :524 */
+    const int e = m < 12 ? anchor + m + 1 : blz_match_end_warp(b, anchor + 12, (int)distance + 1, ip_bound);
+    ip = e - ipshift;                                                        /* :530 */
+    u32 len = (u32)(ip - anchor);
+
+    if (copy) { if (lane == 0) out[op - copy - 1] = (u8)(copy - 1); }        /* :541-546 */
+    else op--;
+    copy = 0;
+    const bool far = distance >= BLZ_MAX_DISTANCE;
+    if (far) distance -= BLZ_MAX_DISTANCE;                                   /* :559 */
+    if (len < 7) {                                                           /* MATCH_SHORT[_FAR] */
+      if (op + (far ? 4 : 2) > op_limit) return 0;
+      if (lane == 0) {
+        if (!far) { out[op] = (u8)((len << 5) + (distance >> 8)); out[op + 1] = (u8)(distance & 255); }
+        else { out[op] = (u8)((len << 5) + 31); out[op + 1] = 255; out[op + 2] = (u8)(distance >> 8); out[op + 3] = (u8)(distance & 255); }
+      }
+      op += far ? 4 : 2;
+    } else {                                                                 /* MATCH_LONG[_FAR] */
+      len -= 7;
+      const int nff = (int)(len / 255);
+      if (op + 1 + nff + (far ? 4 : 2) > op_limit) return 0;
+      if (lane == 0) out[op] = (u8)((7u << 5) + (far ? 31u : (distance >> 8)));
+      op++;
+      warp_fill_bytes(out + op, nff, 255);
+      op += nff;
+      if (lane == 0) {
+        out[op] = (u8)(len - (u32)nff * 255u);
+        if (!far) out[op + 1] = (u8)(distance & 255);
+        else { out[op + 1] = 255; out[op + 2] = (u8)(distance >> 8); out[op + 3] = (u8)(distance & 255); }
+      }
+      op += far ? 4 : 2;
+    }
+    /* update the hash at match boundary (:567-580) */
+    u32 seq = ld_u32(b + ip);
+    if (lane == 0) {
+      tab[blz_hash(seq, hashlog)] = (u32)ip;
+      if (clevel == 9) { seq >>= 8; tab[blz_hash(seq, hashlog)] = (u32)(ip + 1); }
+    }
+    __syncwarp();
+    ip += 2;
+    if (op + 1 > op_limit) return 0;                                         /* :582-586 */
+    if (lane == 0) out[op] = BLZ_MAX_COPY - 1;
+    op++;
+  }
+
+  /* left-over as literal copy (:589-598) */
+  while (ip <= ip_bound) {
+    int nlit = ip_bound - ip + 1;
+    if (nlit > 32) nlit = 32;
+    if (op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2 > op_limit) return 0;
+    if (lane < nlit) {
+      const int o = op + lane + ((copy + lane) >> 5);
+      out[o] = b[ip + lane];
+      if (((copy + lane + 1) & 31) == 0) out[o + 1] = BLZ_MAX_COPY - 1;
+    }
+    op += nlit + ((copy + nlit) >> 5);
+    copy = (copy + nlit) & 31;
+    ip += nlit;
+  }
+  __syncwarp();
+  if (copy) { if (lane == 0) out[op - copy - 1] = (u8)(copy - 1); }          /* :600-604 */
+  else op--;
+  __syncwarp();
+  if (lane == 0) out[0] |= (1u << 5);                                        /* :607 */
+  return op;
+}
+
+/* blosclz_decompress for one stream (blosclz.c:679-789).  Returns bytes written, 0 on error. */
+DEV int blz_decode_warp(const u8* __restrict__ in, const int length, u8* out, const int maxout) {
+  int ip = 0, op = 0;
+  if (length == 0) return 0;
+  u32 ctrl = in[ip++] & 31u;
+  for (;;) {
+    if (ctrl >= 32) {
+      long long len = (long long)(ctrl >> 5) - 1;
+      int ofs = (int)(ctrl & 31u) << 8;
+      long long ref = (long long)op - ofs;
+      u32 code;
+      if (len == 6) {
+        do {
+          if (ip + 1 >= length) return 0;
+          code = in[ip++];
+          len += code;
+        } while (code == 255);
+      } else if (ip + 1 >= length) return 0;
+      code = in[ip++];
+      len += 3;
+      ref -= code;
+      if (code == 255 && ofs == (31 << 8)) {                  /* 16-bit far distance (:717-726) */
+        if (ip + 1 >= length) return 0;
+        ofs = (int)in[ip++] << 8;
+        ofs += in[ip++];
+        ref = (long long)op - ofs - BLZ_MAX_DISTANCE;
+      }
+      if (op + len > maxout) return 0;                        /* :728-730 */
+      if (ref - 1 < 0) return 0;                              /* :732-734 */
+      if (ip >= length) break;                                /* :736 ends without copying */
+      ctrl = in[ip++];
+      ref--;
+      __syncwarp();
+      warp_copy_match(out, op, (int)ref, (int)len);
+      __syncwarp();
+      op += (int)len;
+    } else {
+      ctrl++;
+      if ((long long)op + ctrl > maxout) return 0;            /* :769-774 */
+      if ((long long)ip + ctrl > length) return 0;
+      warp_copy_bytes(out + op, in + ip, (int)ctrl);
+      op += (int)ctrl; ip += (int)ctrl;
+      if (ip >= length) break;
+      ctrl = in[ip++];
+    }
+  }
+  __syncwarp();
+  return op;
+}

@@ -1,0 +1,178 @@
+/*
+ * dev_chunk.cuh -- chunk-level kernels: the GPU replacement of c-blosc's block
+ * scheduler (reference blosc/blosc.c:803-918 serial_blosc/parallel_blosc/do_job and
+ * :1706-1887 t_blosc) and of the per-block pipeline blosc_c / blosc_d (:591-800).
+ *
+ *   encode_kernel   one warp per LZ stream (= one split of one Blosc block): codec into a
+ *                   worst-case slot (capacity neblock, as t_blosc's tmp2, :1810-1811)
+ *   scan_kernel     exclusive scan of the per-block compressed sizes -> bstarts, total
+ *                   cbytes and the "does it fit in destsize" verdict (:1843-1856)
+ *   compact_kernel  writes the 16-byte header, bstarts[] and the int32-prefixed split
+ *                   payloads at their final offsets (:1148-1247, :715, :1860)
+ *   decode_kernel   one warp per LZ stream: bounds-checked walk of the size prefixes
+ *                   (:761-770), raw-split copy or codec (:773-783)
+ */
+#pragma once
+#include "b2_args.h"
+#include "dev_blosclz.cuh"
+#include "dev_common.cuh"
+#include "dev_lz4.cuh"
+
+
+
+/* stream index -> (block, offset inside the uncompressed buffer, length) */
+DEV void stream_locate(const StreamMap& m, int idx, int* block, long long* off, int* len, int* split) {
+  const int nfs = m.nfull * m.nsplits;
+  if (idx < nfs) {
+    const int b = idx / m.nsplits, s = idx - b * m.nsplits;
+    const int neblock = m.blocksize / m.nsplits;
+    *block = m.first_block + b;
+    *off = (long long)(m.first_block + b) * m.blocksize + (long long)s * neblock;
+    *len = neblock;
+    *split = s;
+  } else {
+    *block = m.first_block + m.nfull;
+    *off = (long long)(m.first_block + m.nfull) * m.blocksize;
+    *len = m.leftover;
+    *split = 0;
+  }
+}
+
+
+__global__ void encode_kernel(EncodeArgs a) {
+#ifdef SIMT_EMU
+  u8* smem = simt::g_dynsmem;
+#else
+  extern __shared__ __align__(16) u8 smem[];
+#endif
+  const int warp = (int)(threadIdx.x >> 5), wpc = (int)(blockDim.x >> 5);
+  const int idx = (int)blockIdx.x * wpc + warp;
+  if (idx >= a.map.nstreams) return;
+  void* tab = smem + (size_t)warp * a.table_bytes;
+  int block, len, split;
+  long long off;
+  stream_locate(a.map, idx, &block, &off, &len, &split);
+  const u8* in = a.in + off;
+  u8* out = a.slots + off;
+  int c;
+  if (a.codec == B2_CODEC_LZ4) {
+    if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab);   /* lz4.c:710,1389 */
+    else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab);
+  } else {
+    c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab);
+  }
+  if (c <= 0 || c >= len) c = len;             /* blosc.c:705-714: incompressible split is stored raw */
+  if (lane_id() == 0) a.csizes[idx] = c;
+}
+
+
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
+  __shared__ long long part[SCAN_THREADS];
+  const int tid = (int)threadIdx.x;
+  const int nblocks = a.nfull + (a.has_leftover ? 1 : 0);
+  const int per = (nblocks + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int b0 = tid * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+  long long sum = 0;
+  for (int b = b0; b < b1; b++) {
+    if (b < a.nfull) for (int s = 0; s < a.nsplits; s++) sum += 4 + (long long)a.csizes[(long long)b * a.nsplits + s];
+    else sum += 4 + (long long)a.csizes[(long long)a.nfull * a.nsplits];
+  }
+  part[tid] = sum;
+  __syncthreads();
+  /* Hillis-Steele inclusive scan over the 1024 partials */
+  for (int d = 1; d < SCAN_THREADS; d <<= 1) {
+    const long long v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  long long pos = 16 + 4ll * nblocks + (tid ? part[tid - 1] : 0);
+  for (int b = b0; b < b1; b++) {
+    a.bstarts[b] = (int)(pos > 0x7fffffffll ? 0x7fffffffll : pos);
+    if (b < a.nfull) for (int s = 0; s < a.nsplits; s++) pos += 4 + (long long)a.csizes[(long long)b * a.nsplits + s];
+    else pos += 4 + (long long)a.csizes[(long long)a.nfull * a.nsplits];
+  }
+  if (tid == SCAN_THREADS - 1) {
+    const long long total = 16 + 4ll * nblocks + part[SCAN_THREADS - 1];
+    a.result[0] = (int)(total > 0x7fffffffll ? 0x7fffffffll : total);
+    a.result[1] = total <= a.destsize ? 1 : 0;       /* blosc.c:1848 ntdest+cbytes > maxbytes => give up */
+  }
+}
+
+/* CTA-cooperative copy, any alignment; vectorised when src/dst are mutually aligned */
+DEV void cta_copy_bytes(u8* __restrict__ dst, const u8* __restrict__ src, int n) {
+  const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+  if ((((uintptr_t)dst ^ (uintptr_t)src) & 15u) == 0 && n >= 64) {
+    int head = (int)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    for (int i = tid; i < head; i += nt) dst[i] = src[i];
+    const int nv = (n - head) >> 4;
+    const uint4* s4 = (const uint4*)(src + head);
+    uint4* d4 = (uint4*)(dst + head);
+    for (int i = tid; i < nv; i += nt) d4[i] = s4[i];
+    for (int i = head + (nv << 4) + tid; i < n; i += nt) dst[i] = src[i];
+  } else {
+    for (int i = tid; i < n; i += nt) dst[i] = src[i];
+  }
+}
+
+
+#define COMPACT_THREADS 256
+__global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactArgs a) {
+  if (a.result[1] == 0) return;                 /* does not fit: host falls back to a MEMCPYED chunk */
+  const int tid = (int)threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0) {            /* blosc.c:1154-1215 + :1275 */
+    st_u32_bytes(a.dest, a.hdr0);
+    st_u32_bytes(a.dest + 4, (u32)a.nbytes32);
+    st_u32_bytes(a.dest + 8, (u32)a.map.blocksize);
+    st_u32_bytes(a.dest + 12, (u32)a.result[0]);
+  }
+  for (int b = (int)blockIdx.x; b < a.nblocks; b += (int)gridDim.x) {
+    int pos = a.bstarts[b];
+    if (tid == 0) st_u32_bytes(a.dest + 16 + 4ll * b, (u32)pos);     /* blosc.c:816,1847 */
+    const int ns = b < a.map.nfull ? a.map.nsplits : 1;
+    for (int s = 0; s < ns; s++) {
+      const int idx = b < a.map.nfull ? b * a.map.nsplits + s : a.map.nfull * a.map.nsplits;
+      int blk, len, sp;
+      long long off;
+      stream_locate(a.map, idx, &blk, &off, &len, &sp);
+      const int c = a.csizes[idx];
+      if (tid == 0) st_u32_bytes(a.dest + pos, (u32)c);               /* blosc.c:715 */
+      cta_copy_bytes(a.dest + pos + 4, (c == len ? a.in : a.slots) + off, c);
+      pos += 4 + c;
+    }
+  }
+}
+
+
+DEV int ld_i32(const u8* p) { return (int)ld_u32(p); }
+
+__global__ void decode_kernel(DecodeArgs a) {
+  const int warp = (int)(threadIdx.x >> 5), wpc = (int)(blockDim.x >> 5);
+  const int idx = (int)blockIdx.x * wpc + warp;
+  if (idx >= a.map.nstreams) return;
+  int block, len, split;
+  long long off;
+  stream_locate(a.map, idx, &block, &off, &len, &split);
+  /* walk the size prefixes of this block up to our split (blosc.c:760-771, :784) */
+  int so = ld_i32(a.chunk + 16 + 4ll * block);
+  int cs = 0, err = 0;
+  for (int s = 0; s <= split; s++) {
+    if (so < 0 || so > a.cbytes - 4) { err = B2_ERR_BOUNDS; break; }
+    cs = ld_i32(a.chunk + so);
+    so += 4;
+    if (cs < 0 || cs > a.cbytes - so) { err = B2_ERR_BOUNDS; break; }
+    if (s < split) so += cs;
+  }
+  if (!err) {
+    u8* out = a.out + (off - a.out_shift);
+    const u8* src = a.chunk + so;
+    if (cs == len) warp_copy_bytes(out, src, len);                    /* stored raw, blosc.c:773-776 */
+    else {
+      const int n = a.codec == B2_CODEC_LZ4 ? lz4_decode_warp(src, cs, out, len) : blz_decode_warp(src, cs, out, len);
+      if (n != len) err = B2_ERR_CODEC;                               /* blosc.c:778-782 */
+    }
+  }
+  if (err && lane_id() == 0) atomicMin(a.status, err);
+}

@@ -1,0 +1,109 @@
+/*
+ * dev_common.cuh -- device-side helpers shared by the sm_100a kernels.
+ *
+ * Coding model used by every codec routine in this directory: one warp owns one LZ
+ * stream and behaves like a scalar processor whose registers are replicated in all
+ * 32 lanes (every lane computes the same ip/op/anchor), with explicitly parallel
+ * sections (candidate search, match extension, literal / match copies) where the
+ * lanes fan out and re-converge through a ballot.  Memory writes in the scalar
+ * sections are done by lane 0 only.
+ *
+ * The same sources compile under g++ against tests/emu/simt_emu.h (a lock-step SIMT
+ * emulator used by the CPU test-suite); nothing here depends on that.
+ */
+#pragma once
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#include <stdint.h>
+#endif
+
+typedef unsigned char u8;
+typedef unsigned short u16;
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+#define DEV __device__ __forceinline__
+#define FULLMASK 0xffffffffu
+
+/* status codes written by the decode kernels (mirrors blosc_d's returns, blosc.c:761-782) */
+#define B2_ERR_BOUNDS (-1)
+#define B2_ERR_CODEC (-2)
+
+DEV int lane_id() { return (int)(threadIdx.x & 31u); }
+
+/* Unaligned little-endian 32-bit load. On the GPU: two aligned word loads + funnel
+ * shift (global/shared loads must be naturally aligned). */
+DEV u32 ld_u32(const u8* p) {
+#ifdef SIMT_EMU
+  u32 v; memcpy(&v, p, 4); return v;
+#else
+  const uintptr_t a = (uintptr_t)p;
+  const u32* w = (const u32*)(a & ~(uintptr_t)3);
+  const u32 sh = (u32)(a & 3u) * 8u;
+  const u32 lo = w[0];
+  if (sh == 0) return lo;
+  return __funnelshift_r(lo, w[1], sh);
+#endif
+}
+
+DEV void st_u32_bytes(u8* p, u32 v) {   /* unaligned 32-bit store, byte by byte */
+  p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24);
+}
+
+/* number of equal leading bytes (0..4) given x = a ^ b of two little-endian words */
+DEV int eq_bytes32(u32 x) { return x ? ((__ffs((int)x) - 1) >> 3) : 4; }
+
+/* Warp-parallel common-prefix length: number of i >= 0 with s[p+i] == s[q+i] and
+ * p+i < limit (q < p).  Each lane compares 16 bytes per round; rounds are
+ * independent loads, one ballot each.  Uniform result in all lanes. */
+DEV int warp_count_match(const u8* __restrict__ s, int p, int q, int limit) {
+  const int lane = lane_id();
+  int total = 0;
+  for (;;) {
+    const int i = total + lane * 16;
+    const int avail = limit - (p + i);
+    int eq = 0;
+    if (avail >= 16) {
+      const u32 x0 = ld_u32(s + p + i) ^ ld_u32(s + q + i);
+      const u32 x1 = ld_u32(s + p + i + 4) ^ ld_u32(s + q + i + 4);
+      const u32 x2 = ld_u32(s + p + i + 8) ^ ld_u32(s + q + i + 8);
+      const u32 x3 = ld_u32(s + p + i + 12) ^ ld_u32(s + q + i + 12);
+      if (x0) eq = eq_bytes32(x0);
+      else if (x1) eq = 4 + eq_bytes32(x1);
+      else if (x2) eq = 8 + eq_bytes32(x2);
+      else eq = 12 + eq_bytes32(x3);
+    } else {
+      while (eq < avail && s[p + i + eq] == s[q + i + eq]) eq++;
+    }
+    const unsigned full = __ballot_sync(FULLMASK, eq == 16);
+    if (full == FULLMASK) { total += 512; continue; }
+    const int fl = __ffs((int)~full) - 1;
+    const int e = __shfl_sync(FULLMASK, eq, fl);
+    return total + fl * 16 + e;
+  }
+}
+
+/* Warp-cooperative byte copy between non-overlapping buffers (any alignment). */
+DEV void warp_copy_bytes(u8* __restrict__ dst, const u8* __restrict__ src, int n) {
+  for (int k = lane_id(); k < n; k += 32) dst[k] = src[k];
+}
+
+DEV void warp_fill_bytes(u8* dst, int n, u8 v) {
+  for (int k = lane_id(); k < n; k += 32) dst[k] = v;
+}
+
+/* LZ77 match copy out[op..op+len) = out[match..], forward semantics with overlap
+ * (period = op - match).  Reads only bytes < op, which were written (and made
+ * visible with __syncwarp) before this call, so all lanes are independent. */
+DEV void warp_copy_match(u8* out, int op, int match, int len) {
+  const int off = op - match;
+  const int lane = lane_id();
+  if (off >= len) {
+    for (int k = lane; k < len; k += 32) out[op + k] = out[match + k];
+  } else if (off == 1) {
+    const u8 v = out[match];
+    for (int k = lane; k < len; k += 32) out[op + k] = v;
+  } else {
+    for (int k = lane; k < len; k += 32) out[op + k] = out[match + (k % off)];
+  }
+}

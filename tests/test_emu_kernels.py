@@ -1,0 +1,148 @@
+"""CPU tests of the PRODUCT's device code: the kernels of c-blosc_b200/csrc/dev_*.cuh compiled
+with g++ and run in the lock-step SIMT emulator (tests/emu), and the product's host code
+(blosc_b200.c) linked against that emulated backend.  Everything is compared with the oracle,
+bit for bit.  (The real CUDA build is exercised by the -m gpu tests.)"""
+import numpy as np
+import pytest
+
+from datagen import ci, compress, decompress, gen, ptr, sz
+
+KINDS = ["bench", "rand", "zeros", "lowent", "text", "i32", "mixed"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_lz4_warp_codec(emu, orc, kind):
+    for n in [0, 1, 12, 13, 16, 33, 67, 255, 1000, 5000, 65546, 65547, 100000]:
+        src = gen(kind, n, seed=n)
+        for accel, cap in ((5, n), (1, n), (9, n // 2), (5, n + n // 255 + 16), (5, 70)):
+            a = np.zeros(cap + 64, np.uint8); b = np.zeros(cap + 64, np.uint8)
+            ra = orc.orc_lz4_compress_fast(ptr(src), ptr(a), ci(n), ci(cap), ci(accel))
+            rb = emu.emu_lz4_encode(ptr(src), ci(n), ptr(b), ci(cap), ci(accel))
+            assert ra == rb, (kind, n, accel, cap, ra, rb)
+            if ra > 0:
+                assert (a[:ra] == b[:ra]).all() and (b[ra:] == 0).all()
+                for c2 in (n, n + 3, max(n - 1, 0)):
+                    o1 = np.zeros(n + 8, np.uint8); o2 = np.zeros(n + 8, np.uint8)
+                    d1 = orc.orc_lz4_decompress_safe(ptr(a), ptr(o1), ci(ra), ci(c2))
+                    d2 = emu.emu_lz4_decode(ptr(a), ci(ra), ptr(o2), ci(c2))
+                    assert (d1 < 0) == (d2 < 0) and (d1 < 0 or d1 == d2)
+                    if c2 == n:
+                        assert d2 == n and (o2[:n] == src).all() and (o2[n:] == 0).all()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_blosclz_warp_codec(emu, orc, kind):
+    for n in [0, 15, 16, 17, 33, 67, 128, 255, 1000, 5000, 16500, 70000]:
+        src = gen(kind, n, seed=n)
+        for clevel, split, cap in ((5, 1, n), (5, 0, n), (1, 1, n), (2, 0, n), (9, 1, n), (5, 1, n // 2), (5, 1, 66), (5, 1, 65)):
+            a = np.zeros(cap + 64, np.uint8); b = np.zeros(cap + 64, np.uint8)
+            ra = orc.orc_blosclz_compress(ci(clevel), ptr(src), ci(n), ptr(a), ci(cap), ci(split))
+            rb = emu.emu_blz_encode(ci(clevel), ptr(src), ci(n), ptr(b), ci(cap), ci(split))
+            assert ra == rb, (kind, n, clevel, split, cap, ra, rb)
+            if ra > 0:
+                assert (a[:ra] == b[:ra]).all()
+                o2 = np.zeros(n + 8, np.uint8)
+                assert emu.emu_blz_decode(ptr(a), ci(ra), ptr(o2), ci(n)) == n
+                assert (o2[:n] == src).all() and (o2[n:] == 0).all()
+
+
+def test_decoders_reject_garbage(emu, orc):
+    """Corrupted streams: same accept/reject verdict as the oracle, no out-of-bounds write."""
+    rng = np.random.default_rng(3)
+    src = gen("text", 20000)
+    a = np.zeros(20064, np.uint8)
+    ra = orc.orc_lz4_compress_fast(ptr(src), ptr(a), ci(20000), ci(20000), ci(1))
+    b = np.zeros(20064, np.uint8)
+    rb = orc.orc_blosclz_compress(ci(5), ptr(src), ci(20000), ptr(b), ci(20000), ci(1))
+    for _ in range(150):
+        for buf, n, fo, fe in ((a, ra, "orc_lz4_decompress_safe", "emu_lz4_decode"), (b, rb, "orc_blosclz_decompress", "emu_blz_decode")):
+            c = buf[:n].copy()
+            pos = rng.integers(0, n, 4)
+            c[pos] = rng.integers(0, 256, 4, dtype=np.uint8)
+            o1 = np.zeros(20016, np.uint8); o2 = np.zeros(20016, np.uint8)
+            if fo.startswith("orc_lz4"):
+                d1 = getattr(orc, fo)(ptr(c), ptr(o1), ci(n), ci(20000)); d2 = getattr(emu, fe)(ptr(c), ci(n), ptr(o2), ci(20000))
+            else:
+                d1 = getattr(orc, fo)(ptr(c), ci(n), ptr(o1), ci(20000)); d2 = getattr(emu, fe)(ptr(c), ci(n), ptr(o2), ci(20000))
+            assert (d1 <= 0) == (d2 <= 0) or d1 == d2, (fo, d1, d2)
+            if d1 > 0 and d1 == d2:
+                assert (o1[:d1] == o2[:d1]).all()
+            assert (o2[20000:] == 0).all()
+
+
+@pytest.mark.parametrize("dev", [0, 1])
+def test_filter_kernels(emu, orc, dev):
+    """dev=1 makes the emulated backend treat caller pointers as device pointers (no staging copy),
+    so misaligned user buffers reach the kernels directly."""
+    emu.emu_set_all_device(dev)
+    try:
+        for ts in [1, 2, 3, 4, 5, 8, 16, 17]:
+            for n in [0, 1, 7, 8, 64, 500, 1792, 8000, 8192, 32768, 100000, 131072, 131072 + 24]:
+                base = gen("rand", n + 3, seed=ts)
+                for off in ((0, 1) if dev else (0,)):
+                    src = base[off:off + n]
+                    for mode, fn in enumerate(["orc_shuffle", "orc_unshuffle", "orc_bitshuffle", "orc_bitunshuffle"]):
+                        if mode >= 2 and n < ts:
+                            continue
+                        a = np.zeros(n + 1, np.uint8); b = np.zeros(n + 1, np.uint8)
+                        getattr(orc, fn)(sz(ts), sz(n), ptr(src), ptr(a))
+                        assert emu.blosc_b200_filter(ci(mode), sz(ts), sz(n), ptr(src), ptr(b)) == 0
+                        assert (a == b).all(), (fn, ts, n, dev, off)
+    finally:
+        emu.emu_set_all_device(0)
+
+
+@pytest.mark.parametrize("kind", ["bench", "i32", "mixed", "rand"])
+def test_library_against_oracle(emu, orc, kind):
+    """Host framing + every kernel: chunks identical to the oracle's, decode, getitem."""
+    for dev in (0, 1):
+        emu.emu_set_all_device(dev)
+        try:
+            for n in ([0, 1, 100, 128, 129, 1000, 4096, 32768, 100000, 300000] if dev == 0 else [129, 4096, 100000]):
+                src = gen(kind, n, seed=n)
+                for comp in ("lz4", "blosclz"):
+                    for ts, shuf, clevel, bs in ((4, 1, 5, 0), (8, 2, 5, 0), (1, 0, 5, 0), (2, 1, 9, 0), (16, 1, 1, 0), (7, 1, 5, 0), (17, 2, 5, 0),
+                                                 (4, 2, 5, 4096), (4, 1, 0, 0), (256, 1, 5, 0), (3, 2, 9, 100)):
+                        ra, a = compress(orc, "orc_compress_ctx", clevel, shuf, ts, src, n + 16, comp, bs)
+                        rb, b = compress(emu, "blosc_compress_ctx", clevel, shuf, ts, src, n + 16, comp, bs)
+                        assert ra == rb, (kind, n, comp, ts, shuf, clevel, bs, ra, rb)
+                        if ra <= 0:
+                            continue
+                        assert (a[:ra] == b[:ra]).all() and (b[ra:] == 0xAA).all()
+                        d2, o2 = decompress(emu, "blosc_decompress_ctx", a, n)
+                        assert d2 == n and (o2[:n] == src).all()
+                        if 0 < n <= 100000:
+                            nit = n // int(a[3])
+                            for st, cnt in ((0, nit), (nit // 3, nit // 2), (nit - 1, 1), (0, 0)):
+                                g1 = np.zeros(n + 8, np.uint8); g2 = np.zeros(n + 8, np.uint8)
+                                r1 = orc.orc_getitem(ptr(a), ci(st), ci(cnt), ptr(g1))
+                                r2 = emu.blosc_getitem(ptr(a), ci(st), ci(cnt), ptr(g2))
+                                assert r1 == r2 and (g1 == g2).all()
+        finally:
+            emu.emu_set_all_device(0)
+
+
+def test_library_error_codes(emu):
+    src = gen("rand", 100000)
+    n = len(src)
+    assert compress(emu, "blosc_compress_ctx", 5, 1, 4, src, n + 15, "lz4")[0] == 0
+    assert compress(emu, "blosc_compress_ctx", 5, 1, 4, src, n + 16, "lz4")[0] == n + 16
+    assert compress(emu, "blosc_compress_ctx", 5, 1, 4, src, 15, "lz4")[0] == 0
+    assert compress(emu, "blosc_compress_ctx", 11, 1, 4, src, n + 16, "lz4")[0] == -10
+    assert compress(emu, "blosc_compress_ctx", 5, 4, 4, src, n + 16, "lz4")[0] == -10
+    assert compress(emu, "blosc_compress_ctx", 5, 1, 0, src, n + 16, "lz4")[0] == -10
+    assert compress(emu, "blosc_compress_ctx", 5, 1, 4, src, n + 16, "zstd")[0] == -5
+    big = gen("rand", 300000)      # > 1 block, so the reference would take the pool path and validate nthreads
+    assert compress(emu, "blosc_compress_ctx", 5, 0, 1, big, len(big) + 16, "lz4", 0, 0)[0] == -1
+    assert compress(emu, "blosc_compress_ctx", 5, 0, 1, big, len(big) + 16, "lz4", 0, 257)[0] == -1
+    assert compress(emu, "blosc_compress_ctx", 5, 1, 4, src, n + 16, "lz4", 0, 0)[0] == n + 16   # single block: serial path, no check
+    cb, chunk = compress(emu, "blosc_compress_ctx", 5, 1, 4, gen("bench", n), n + 16, "lz4")
+    c = chunk.copy(); c[0] = 3
+    assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -1
+    c = chunk.copy(); c[1] = 2
+    assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -9
+    c = chunk.copy(); c[2] = (c[2] & 0x1f) | (4 << 5)
+    assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -5
+    assert decompress(emu, "blosc_decompress_ctx", chunk, n - 1)[0] == -1
+    c = chunk.copy(); c[20:24] = 0xff
+    assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -1

@@ -113,8 +113,11 @@ def test_maxout_semantics(pkg, cuda):
     assert _gpu_compress(pkg, 5, 3, 4, src, n + 16, "blosclz")[0] == -10
     assert _gpu_compress(pkg, 5, 1, 0, src, n + 16, "blosclz")[0] == -10
     assert _gpu_compress(pkg, 5, 1, 4, src, n + 16, "snappy")[0] == -5
-    assert _gpu_compress(pkg, 5, 1, 4, src, n + 16, "lz4", 0, 0)[0] == -1
-    assert _gpu_compress(pkg, 5, 1, 4, src, n + 16, "lz4", 0, 300)[0] == -1
+    # nthreads is validated only where the reference takes its pool path (more than one block, blosc.c:910)
+    assert _gpu_compress(pkg, 5, 1, 4, src, n + 16, "lz4", 0, 0)[0] == n + 16
+    big = gen("rand", 4 << 20, seed=2)
+    assert _gpu_compress(pkg, 5, 1, 4, big, len(big) + 16, "lz4", 0, 0)[0] == -1
+    assert _gpu_compress(pkg, 5, 1, 4, big, len(big) + 16, "lz4", 0, 300)[0] == -1
 
 
 def test_compat_golden_chunks(pkg, cuda):

@@ -39,6 +39,7 @@ typedef struct EncodeArgs {
   int* csizes;           /* [nstreams] compressed size; == stream length means "stored raw" */
   int codec, clevel, accel, split_flag;
   int table_bytes;       /* shared-memory bytes per warp */
+  int* queue;            /* zero-initialised work counter: warps pull stream numbers from it */
 } EncodeArgs;
 
 typedef struct ScanArgs {
@@ -69,6 +70,7 @@ typedef struct DecodeArgs {
   long long out_shift;   /* subtracted from the buffer offset (getitem decodes into a small scratch) */
   int codec;
   int* status;           /* 0 ok, else min of the negative error codes */
+  int* queue;            /* zero-initialised work counter */
 } DecodeArgs;
 
 #ifdef __cplusplus

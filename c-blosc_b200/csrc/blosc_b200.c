@@ -52,7 +52,7 @@ typedef struct {
   int in_use, ready, dev;
   b2_stream_t stream;
   b2_buf in, filt, slots, out, csizes, bstarts;
-  int* d_result;        /* [0] cbytes [1] fits [2] decode status */
+  int* d_result;        /* [0] cbytes [1] fits [2] decode status [3] work-queue counter */
   int* h_result;        /* pinned mirror */
 } b2_ws;
 
@@ -392,6 +392,8 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
     ea.split_flag = !dont_split;
     ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
+    ea.queue = w->d_result + 3;
+    if (b2_memset_dev(ea.queue, 0, 4, w->stream)) break;
     if (b2_launch_encode(&ea, w->stream)) break;
     sa.csizes = ea.csizes; sa.bstarts = (int*)w->bstarts.p; sa.result = w->d_result;
     sa.nsplits = nsplits; sa.nfull = nfull; sa.has_leftover = leftover > 0; sa.destsize = dsz;
@@ -474,9 +476,9 @@ static int decode_blocks(b2_ws* w, const b2_hdr* h, int codec, const uint8_t* d_
     if (buf_ensure(&w->filt, (size_t)span + 64)) return -1;
     d_codec_out = (uint8_t*)w->filt.p;
   }
-  if (b2_memset_dev(w->d_result + 2, 0, 4, w->stream)) return -1;
+  if (b2_memset_dev(w->d_result + 2, 0, 8, w->stream)) return -1;   /* status + work-queue counter */
   da.chunk = d_chunk; da.cbytes = h->cbytes; da.out = d_codec_out; da.out_shift = (long long)first * bs;
-  da.codec = codec; da.status = w->d_result + 2;
+  da.codec = codec; da.status = w->d_result + 2; da.queue = w->d_result + 3;
   if (b2_launch_decode(&da, w->stream)) return -1;
   if (doshuffle || dobitshuffle) {
     fa.src = d_codec_out; fa.dst = d_out; fa.nbytes = span; fa.blocksize = bs; fa.typesize = ts;

@@ -20,6 +20,26 @@
 
 
 
+/* Dynamic scheduling (the GPU counterpart of t_blosc's shared block counter, blosc.c:1769-1776):
+ * every warp pulls the next job number from a global counter until none is left.  Jobs are
+ * numbered longest-first as far as that is knowable without looking at the data: the unsplit
+ * leftover block first, then split-major (split s of every block before split s+1), so that
+ * the byte-planes that turn out to be hard start in the first wave and the cheap ones fill in
+ * behind them.  Returns the stream index, or -1 when the queue is empty. */
+DEV int next_stream(int* queue, const StreamMap& m) {
+  int job = 0;
+  if (lane_id() == 0) job = atomicAdd(queue, 1);
+  job = __shfl_sync(FULLMASK, job, 0);
+  if (job >= m.nstreams) return -1;
+  const int nfs = m.nfull * m.nsplits;
+  if (m.leftover) {
+    if (job == 0) return nfs;
+    job--;
+  }
+  const int s = job / m.nfull, b = job - s * m.nfull;
+  return b * m.nsplits + s;
+}
+
 /* stream index -> (block, offset inside the uncompressed buffer, length) */
 DEV void stream_locate(const StreamMap& m, int idx, int* block, long long* off, int* len, int* split) {
   const int nfs = m.nfull * m.nsplits;
@@ -45,24 +65,27 @@ __global__ void encode_kernel(EncodeArgs a) {
 #else
   extern __shared__ __align__(16) u8 smem[];
 #endif
-  const int warp = (int)(threadIdx.x >> 5), wpc = (int)(blockDim.x >> 5);
-  const int idx = (int)blockIdx.x * wpc + warp;
-  if (idx >= a.map.nstreams) return;
+  const int warp = (int)(threadIdx.x >> 5);
   void* tab = smem + (size_t)warp * a.table_bytes;
-  int block, len, split;
-  long long off;
-  stream_locate(a.map, idx, &block, &off, &len, &split);
-  const u8* in = a.in + off;
-  u8* out = a.slots + off;
-  int c;
-  if (a.codec == B2_CODEC_LZ4) {
-    if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab);   /* lz4.c:710,1389 */
-    else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab);
-  } else {
-    c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab);
+  for (;;) {
+    const int idx = next_stream(a.queue, a.map);
+    if (idx < 0) return;
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    const u8* in = a.in + off;
+    u8* out = a.slots + off;
+    int c;
+    if (a.codec == B2_CODEC_LZ4) {
+      if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab);   /* lz4.c:710,1389 */
+      else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab);
+    } else {
+      c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab);
+    }
+    if (c <= 0 || c >= len) c = len;           /* blosc.c:705-714: incompressible split is stored raw */
+    if (lane_id() == 0) a.csizes[idx] = c;
+    __syncwarp();
   }
-  if (c <= 0 || c >= len) c = len;             /* blosc.c:705-714: incompressible split is stored raw */
-  if (lane_id() == 0) a.csizes[idx] = c;
 }
 
 
@@ -148,31 +171,42 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactArgs a)
 
 DEV int ld_i32(const u8* p) { return (int)ld_u32(p); }
 
-__global__ void decode_kernel(DecodeArgs a) {
-  const int warp = (int)(threadIdx.x >> 5), wpc = (int)(blockDim.x >> 5);
-  const int idx = (int)blockIdx.x * wpc + warp;
-  if (idx >= a.map.nstreams) return;
-  int block, len, split;
-  long long off;
-  stream_locate(a.map, idx, &block, &off, &len, &split);
-  /* walk the size prefixes of this block up to our split (blosc.c:760-771, :784) */
-  int so = ld_i32(a.chunk + 16 + 4ll * block);
-  int cs = 0, err = 0;
-  for (int s = 0; s <= split; s++) {
-    if (so < 0 || so > a.cbytes - 4) { err = B2_ERR_BOUNDS; break; }
-    cs = ld_i32(a.chunk + so);
-    so += 4;
-    if (cs < 0 || cs > a.cbytes - so) { err = B2_ERR_BOUNDS; break; }
-    if (s < split) so += cs;
-  }
-  if (!err) {
-    u8* out = a.out + (off - a.out_shift);
-    const u8* src = a.chunk + so;
-    if (cs == len) warp_copy_bytes(out, src, len);                    /* stored raw, blosc.c:773-776 */
-    else {
-      const int n = a.codec == B2_CODEC_LZ4 ? lz4_decode_warp(src, cs, out, len) : blz_decode_warp(src, cs, out, len);
-      if (n != len) err = B2_ERR_CODEC;                               /* blosc.c:778-782 */
+#define DECODE_WARPS 4
+/* dynamic shared memory: DECODE_WARPS * LZ4D_RING bytes (per-warp ring of recent output) */
+__global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a) {
+#ifdef SIMT_EMU
+  u8* smem = simt::g_dynsmem;
+#else
+  extern __shared__ __align__(16) u8 smem[];
+#endif
+  const int warp = (int)(threadIdx.x >> 5);
+  for (;;) {
+    const int idx = next_stream(a.queue, a.map);
+    if (idx < 0) return;
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    /* walk the size prefixes of this block up to our split (blosc.c:760-771, :784) */
+    int so = ld_i32(a.chunk + 16 + 4ll * block);
+    int cs = 0, err = 0;
+    for (int s = 0; s <= split; s++) {
+      if (so < 0 || so > a.cbytes - 4) { err = B2_ERR_BOUNDS; break; }
+      cs = ld_i32(a.chunk + so);
+      so += 4;
+      if (cs < 0 || cs > a.cbytes - so) { err = B2_ERR_BOUNDS; break; }
+      if (s < split) so += cs;
     }
+    if (!err) {
+      u8* out = a.out + (off - a.out_shift);
+      const u8* src = a.chunk + so;
+      if (cs == len) warp_copy_bytes(out, src, len);                    /* stored raw, blosc.c:773-776 */
+      else {
+        const int n = a.codec == B2_CODEC_LZ4 ? lz4_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_RING)
+                                               : blz_decode_warp(src, cs, out, len);
+        if (n != len) err = B2_ERR_CODEC;                               /* blosc.c:778-782 */
+      }
+    }
+    if (err && lane_id() == 0) atomicMin(a.status, err);
+    __syncwarp();
   }
-  if (err && lane_id() == 0) atomicMin(a.status, err);
 }

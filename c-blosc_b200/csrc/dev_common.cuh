@@ -46,6 +46,26 @@ DEV u32 ld_u32(const u8* p) {
 #endif
 }
 
+/* Shared-memory byte access through a 32-bit shared-window address (no generic->shared
+ * conversion in the inner loops).  In the emulator a "shared address" is a plain pointer. */
+#ifdef SIMT_EMU
+typedef u8* smem_addr_t;
+DEV smem_addr_t smem_addr(void* p) { return (u8*)p; }
+DEV u32 smem_ld_u8(smem_addr_t base, u32 off) { return base[off]; }
+DEV void smem_st_u8(smem_addr_t base, u32 off, u32 v) { base[off] = (u8)v; }
+#else
+typedef u32 smem_addr_t;
+DEV smem_addr_t smem_addr(void* p) { return (u32)__cvta_generic_to_shared(p); }
+DEV u32 smem_ld_u8(smem_addr_t base, u32 off) {
+  u32 v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + off));
+  return v;
+}
+DEV void smem_st_u8(smem_addr_t base, u32 off, u32 v) {
+  asm volatile("st.shared.u8 [%0], %1;" :: "r"(base + off), "r"(v) : "memory");
+}
+#endif
+
 DEV void st_u32_bytes(u8* p, u32 v) {   /* unaligned 32-bit store, byte by byte */
   p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24);
 }
@@ -92,12 +112,40 @@ DEV void warp_fill_bytes(u8* dst, int n, u8 v) {
   for (int k = lane_id(); k < n; k += 32) dst[k] = v;
 }
 
+/* Long periodic fill: out[op+k] = out[match + k % off] for k < len when the period `off`
+ * is a power of two <= 512 (the byte/bit-shuffled planes Blosc feeds the codecs are full of
+ * these: zero planes are off==1 runs, the bench.c planes repeat with period 256).  Each
+ * lane's 16-byte phase is then loop invariant: gather it once, store aligned uint4s. */
+DEV void warp_fill_period_pow2(u8* out, int op, int match, int len) {
+  const int off = op - match;
+  const int lane = lane_id();
+  int head = (int)((16u - (u32)((uintptr_t)(out + op) & 15u)) & 15u);
+  if (head > len) head = len;
+  for (int k = lane; k < head; k += 32) out[op + k] = out[match + (k & (off - 1))];
+  const int body = (len - head) & ~15;
+  if (body > 0) {
+    u32 w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      u32 v = 0;
+#pragma unroll
+      for (int t = 0; t < 4; t++) v |= (u32)out[match + ((head + 16 * lane + 4 * q + t) & (off - 1))] << (8 * t);
+      w[q] = v;
+    }
+    const uint4 pat = make_uint4(w[0], w[1], w[2], w[3]);
+    uint4* dst = (uint4*)(out + op + head);
+    for (int c = lane; c < (body >> 4); c += 32) dst[c] = pat;     /* 512 % off == 0: same phase every round */
+  }
+  for (int k = head + body + lane; k < len; k += 32) out[op + k] = out[match + (k & (off - 1))];
+}
+
 /* LZ77 match copy out[op..op+len) = out[match..], forward semantics with overlap
  * (period = op - match).  Reads only bytes < op, which were written (and made
  * visible with __syncwarp) before this call, so all lanes are independent. */
 DEV void warp_copy_match(u8* out, int op, int match, int len) {
   const int off = op - match;
   const int lane = lane_id();
+  if (len >= 96 && off <= 512 && (off & (off - 1)) == 0) { warp_fill_period_pow2(out, op, match, len); return; }
   if (off >= len) {
     for (int k = lane; k < len; k += 32) out[op + k] = out[match + k];
   } else if (off == 1) {

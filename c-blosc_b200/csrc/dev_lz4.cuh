@@ -38,13 +38,96 @@ DEV long long lz4_probe_offset(int it, int accel) {
   return 1 + m * accel + 32 * c * (c - 1) + c * (m - 64 * c);
 }
 
+/* 12 consecutive bytes starting at q (any alignment) as three little-endian words.
+ * GPU: four aligned word loads + funnel shifts; it may touch the aligned words around
+ * [q, q+12), i.e. up to q+15 -- callers guarantee q+16 <= end of the stream. */
+DEV void ld_win12(const u8* q, u32& b0, u32& b1, u32& b2) {
+#ifdef SIMT_EMU
+  memcpy(&b0, q, 4); memcpy(&b1, q + 4, 4); memcpy(&b2, q + 8, 4);
+#else
+  const uintptr_t a = (uintptr_t)q;
+  const u32* w = (const u32*)(a & ~(uintptr_t)3);
+  const u32 sh = (u32)(a & 3u) * 8u;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
+#endif
+}
+
+/* 8 consecutive bytes at q; touches at most q+11 */
+DEV void ld_win8(const u8* q, u32& b0, u32& b1) {
+#ifdef SIMT_EMU
+  memcpy(&b0, q, 4); memcpy(&b1, q + 4, 4);
+#else
+  const uintptr_t a = (uintptr_t)q;
+  const u32* w = (const u32*)(a & ~(uintptr_t)3);
+  const u32 sh = (u32)(a & 3u) * 8u;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
+#endif
+}
+
+/* Position-based window loads: the stream base is split once into an aligned word pointer
+ * (s32) and a byte phase (sal); a window at byte position p then costs one 64-bit address
+ * computation (IMAD.WIDE) instead of one per word. */
+struct StreamBase {
+  const u8* s;
+  const u32* s32;
+  int sal;
+};
+DEV StreamBase make_stream_base(const u8* s) {
+  StreamBase b;
+  b.s = s;
+  b.s32 = (const u32*)((uintptr_t)s & ~(uintptr_t)3);
+  b.sal = (int)((uintptr_t)s & 3u);
+  return b;
+}
+DEV void ldp_win12(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2) {
+#ifdef SIMT_EMU
+  memcpy(&b0, sb.s + p, 4); memcpy(&b1, sb.s + p + 4, 4); memcpy(&b2, sb.s + p + 8, 4);
+#else
+  const int q = p + sb.sal;
+  const u32* w = sb.s32 + (q >> 2);
+  const u32 sh = (u32)(q & 3) * 8u;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
+#endif
+}
+DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
+#ifdef SIMT_EMU
+  memcpy(&b0, sb.s + p, 4); memcpy(&b1, sb.s + p + 4, 4);
+#else
+  const int q = p + sb.sal;
+  const u32* w = sb.s32 + (q >> 2);
+  const u32 sh = (u32)(q & 3) * 8u;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
+#endif
+}
+
+template <bool U16>
+DEV u32 lz4_hash_seq(u32 lo, u32 b4) {                        /* lz4.c:777-806 on bytes already in registers */
+  if (U16) return (lo * 2654435761u) >> (32 - 13);
+  const u64 seq = (u64)lo | ((u64)(b4 & 0xffu) << 32);
+  return (u32)(((seq << 24) * 889523592379ull) >> (64 - 12));
+}
+
 /* Returns the compressed size, or 0 when the stream does not fit in `cap`
  * (LZ4_compress_fast's limitedOutput failure).  Uniform across the warp.
- * `tabmem` is LZ4_TABLE_BYTES of shared memory private to this warp. */
+ * `tabmem` is LZ4_TABLE_BYTES of shared memory private to this warp.
+ *
+ * Hot-path shape (driven by the ncu source view of v1: ~250 dependent warp instructions
+ * per sequence on the hard byte-plane): everything uniform across the warp is executed
+ * redundantly by all lanes -- including the hash-table stores, so the scalar sections
+ * need no broadcast and no __syncwarp.  The first two probes of every search and the
+ * "test next position" probe are scalar and work on 12-byte register windows (one round of
+ * aligned loads each); a sequence with < 15 literals and a short match is written by ONE
+ * predicated store (lane 0 = token, lanes 1..lit = literals, the next two = offset).  The
+ * 32-wide probe rounds only run when the first two probes miss. */
 template <bool U16>
 DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ d, const int cap,
                         const int accel, void* tabmem) {
   const int lane = lane_id();
+  const StreamBase sb = make_stream_base(s);
   u16* tab16 = (u16*)tabmem;
   u32* tab32 = (u32*)tabmem;
 #define LZ4_TGET(h) (U16 ? (int)tab16[h] : (int)tab32[h])
@@ -58,111 +141,177 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   const int mfl1 = n - LZ4_MFLIMIT + 1;       /* mflimitPlusOne */
   const int matchlimit = n - LZ4_LASTLITERALS;
   int ip = 1, anchor = 0, op = 0;
-  bool more = n >= LZ4_MFLIMIT + 1;           /* lz4.c:1002 */
   /* first byte (lz4.c:1005-1010): table[hash(0)] = 0, which the zeroed table already says */
 
-  while (more) {
-    /* ---- find a match: 32 probes per round ---- */
-    int match = 0;
-    bool found_any = false;
-    for (int base_it = 0;; base_it += 32) {
-      const int it = base_it + lane;
-      const bool valid = ip + lz4_probe_offset(it + 1, accel) <= mfl1;   /* else: `goto _last_literals` (lz4.c:1055) */
-      const int pos = valid ? ip + (int)lz4_probe_offset(it, accel) : 0;
-      u32 h = 0x80000000u | (u32)lane, seq = 0;
-      if (valid) { seq = ld_u32(s + pos); h = lz4_hash_at<U16>(s, pos); }
-      const unsigned vmask = __ballot_sync(FULLMASK, valid);
-      const unsigned peers = __match_any_sync(FULLMASK, h);
-      const unsigned lower = peers & ((1u << lane) - 1u);
-      int cand = 0;
-      bool hit = false;
-      if (valid) {
-        cand = lower ? ip + (int)lz4_probe_offset(base_it + (31 - __clz((int)lower)), accel) : LZ4_TGET(h);
-        if (U16 || cand + 65535 >= pos) hit = ld_u32(s + cand) == seq;       /* lz4.c:1090-1101 */
-      }
-      const unsigned found = __ballot_sync(FULLMASK, hit);
-      const int nvalid = __popc(vmask);                       /* valid lanes form a prefix */
-      const int f = found ? __ffs((int)found) - 1 : 32;
-      const int last = f < nvalid - 1 ? f : nvalid - 1;       /* last probe committed to the table */
-      if (valid && lane <= last) {
-        const unsigned le = last >= 31 ? FULLMASK : ((1u << (last + 1)) - 1u);
-        if ((((peers & le) >> lane) >> 1) == 0) LZ4_TPUT(h, pos);  /* highest committed lane per hash wins */
-      }
-      __syncwarp();
-      if (found) {
-        ip = __shfl_sync(FULLMASK, pos, f);
-        match = __shfl_sync(FULLMASK, cand, f);
-        found_any = true;
-        break;
-      }
-      if (nvalid < 32) break;                                  /* ran into the end: last literals */
-    }
-    if (!found_any) break;
-
-    /* ---- catch up (lz4.c:1107-1109) ---- */
+  if (n >= LZ4_MFLIMIT + 1) {                 /* lz4.c:1002 */
+    bool post = false;                        /* true: a match just ended at ip (== anchor) */
     for (;;) {
-      const int a = ip - 1 - lane, b = match - 1 - lane;
-      const bool ok = a >= anchor && b >= 0 && s[a] == s[b];
-      const unsigned m = __ballot_sync(FULLMASK, ok);
-      const int back = m == FULLMASK ? 32 : __ffs((int)~m) - 1;
-      ip -= back; match -= back;
-      if (back < 32) break;
-    }
+      int match = 0, lit = 0, back = 0;
+      u32 ipn = 0, cn = 0;                    /* bytes [ip+4, ip+8) and [match+4, match+8) of the hit */
+      bool have_next = false, hit = false, imm = false;
 
-    /* ---- literals (lz4.c:1112-1136) ---- */
-    const int lit = ip - anchor;
-    int token = op++;
-    if (limited && op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255 > olimit) return 0;
-    u32 tokval;
-    if (lit >= 15) {
-      const int len = lit - 15, nff = len / 255;
-      tokval = 15u << 4;
-      warp_fill_bytes(d + op, nff, 255);
-      if (lane == 0) d[op + nff] = (u8)(len - nff * 255);
-      op += nff + 1;
-    } else tokval = (u32)lit << 4;
-    warp_copy_bytes(d + op, s + anchor, lit);
-    op += lit;
+      if (post) {
+        /* ---- fill table at ip-2, test position ip (lz4.c:1236-1294); no literals on a hit ---- */
+        u32 b0, b1, b2 = 0;
+        const bool wide = ip + 14 <= n;
+        if (wide) ldp_win12(sb, ip - 2, b0, b1, b2);
+        else { b0 = ld_u32(s + ip - 2); b1 = ld_u32(s + ip + 2); }
+        const u32 seq = __funnelshift_r(b0, b1, 16);                       /* bytes ip .. ip+3 */
+        const u32 h2 = lz4_hash_seq<U16>(b0, b1);                          /* 5th byte of ip-2 is s[ip+2] */
+        const u32 h = lz4_hash_seq<U16>(seq, b1 >> 16);                    /* 5th byte of ip is s[ip+4] */
+        LZ4_TPUT(h2, ip - 2);
+        const int cand = LZ4_TGET(h);
+        __syncwarp();                      /* every lane has read the old entry before any lane overwrites it */
+        LZ4_TPUT(h, ip);
+        if (U16 || cand + 65535 >= ip) {
+          u32 c0, c1;
+          ldp_win8(sb, cand, c0, c1);
+          if (c0 == seq) {
+            hit = true; imm = true; match = cand;
+            ipn = __funnelshift_r(b1, b2, 16); cn = c1; have_next = wide;
+          }
+        }
+        if (!hit) ip++;                                                    /* lz4.c:1298 */
+      }
 
-    for (;;) {   /* _next_match (lz4.c:1138-1226) */
+      if (!hit) {
+        /* ---- find a match (lz4.c:1043-1101): two scalar probes, then 32-wide rounds ---- */
+        bool ended = false;
+        for (int it = 0; it < 2; it++) {
+          const int pos = ip + (it ? 1 : 0);                               /* probe offsets 0, 1 */
+          if (ip + (it ? 1 + accel : 1) > mfl1) { ended = true; break; }   /* `goto _last_literals` (lz4.c:1055) */
+          u32 b0, b1 = 0, b2 = 0;
+          const bool wide = pos + 16 <= n;
+          if (wide) ldp_win12(sb, pos, b0, b1, b2);
+          else { b0 = ld_u32(s + pos); b1 = (u32)s[pos + 4]; }
+          const u32 h = lz4_hash_seq<U16>(b0, b1);
+          const int cand = LZ4_TGET(h);
+          __syncwarp();
+          LZ4_TPUT(h, pos);
+          if (U16 || cand + 65535 >= pos) {
+            u32 c0, c1;
+            ldp_win8(sb, cand, c0, c1);
+            if (c0 == b0) {
+              hit = true; ip = pos; match = cand;
+              ipn = b1; cn = c1; have_next = wide;
+              break;
+            }
+          }
+        }
+        if (!hit && !ended) {
+          for (int base_it = 2;; base_it += 32) {
+            const int itl = base_it + lane;
+            const bool valid = ip + lz4_probe_offset(itl + 1, accel) <= mfl1;
+            const int pos = valid ? ip + (int)lz4_probe_offset(itl, accel) : 0;
+            u32 h = 0x80000000u | (u32)lane, seq = 0;
+            if (valid) { seq = ld_u32(s + pos); h = lz4_hash_at<U16>(s, pos); }
+            const unsigned vmask = __ballot_sync(FULLMASK, valid);
+            const unsigned peers = __match_any_sync(FULLMASK, h);
+            const unsigned lower = peers & ((1u << lane) - 1u);
+            int cand = 0;
+            bool lhit = false;
+            if (valid) {
+              cand = lower ? ip + (int)lz4_probe_offset(base_it + (31 - __clz((int)lower)), accel) : LZ4_TGET(h);
+              if (U16 || cand + 65535 >= pos) lhit = ld_u32(s + cand) == seq;   /* lz4.c:1090-1101 */
+            }
+            const unsigned found = __ballot_sync(FULLMASK, lhit);
+            const int nvalid = __popc(vmask);                       /* valid lanes form a prefix */
+            const int f = found ? __ffs((int)found) - 1 : 32;
+            const int last = f < nvalid - 1 ? f : nvalid - 1;       /* last probe committed to the table */
+            if (valid && lane <= last) {
+              const unsigned le = last >= 31 ? FULLMASK : ((1u << (last + 1)) - 1u);
+              if ((((peers & le) >> lane) >> 1) == 0) LZ4_TPUT(h, pos);  /* highest committed lane per hash wins */
+            }
+            __syncwarp();
+            if (found) {
+              ip = __shfl_sync(FULLMASK, pos, f);
+              match = __shfl_sync(FULLMASK, cand, f);
+              hit = true;
+              break;
+            }
+            if (nvalid < 32) break;                                  /* ran into the end: last literals */
+          }
+        }
+        if (!hit) break;                                             /* -> last literals */
+
+        /* ---- catch up (lz4.c:1107-1109) ---- */
+        if (ip > anchor && match > 0 && s[ip - 1] == s[match - 1]) {
+          for (;;) {
+            const int a = ip - 1 - back - lane, b = match - 1 - back - lane;
+            const bool ok = a >= anchor && b >= 0 && s[a] == s[b];
+            const unsigned m = __ballot_sync(FULLMASK, ok);
+            const int step = m == FULLMASK ? 32 : __ffs((int)~m) - 1;
+            back += step;
+            if (step < 32) break;
+          }
+        }
+        lit = ip - back - anchor;
+      }
+
+      /* ---- match length (lz4.c:1182-1184): LZ4_count(start+4, ...) = catch-up bytes + forward bytes.
+       * Most matches of shuffled data are 8..20 bytes long: compare that much with scalar
+       * (warp-uniform) loads first and only then fall into the 512-bytes-per-round warp loop. ---- */
+      int mc;
+      {
+        const int room = matchlimit - (ip + 4);                      /* >= 3 because ip < mflimitPlusOne */
+        if (have_next) {
+          const u32 x = ipn ^ cn;
+          if (x) mc = eq_bytes32(x);
+          else if (room > 20) {
+            u32 p0, p1, p2, q0, q1, q2;                              /* bytes [ip+8, ip+20) vs [match+8, match+20) */
+            ldp_win12(sb, ip + 8, p0, p1, p2);                        /* ip+8+16 <= n because room > 20 */
+            ldp_win12(sb, match + 8, q0, q1, q2);
+            const u32 x0 = p0 ^ q0, x1 = p1 ^ q1, x2 = p2 ^ q2;
+            if (x0) mc = 4 + eq_bytes32(x0);
+            else if (x1) mc = 8 + eq_bytes32(x1);
+            else if (x2) mc = 12 + eq_bytes32(x2);
+            else mc = 16 + warp_count_match(s, ip + 20, match + 20, matchlimit);
+          } else mc = 4 + (room > 4 ? warp_count_match(s, ip + 8, match + 8, matchlimit) : 0);
+          if (mc > room) mc = room;
+        } else mc = warp_count_match(s, ip + 4, match + 4, matchlimit);
+      }
       const int off = ip - match;
-      if (lane == 0) { d[op] = (u8)off; d[op + 1] = (u8)(off >> 8); }
-      op += 2;
-      int mc = warp_count_match(s, ip + 4, match + 4, matchlimit);
       ip += mc + 4;
-      if (limited && op + (1 + LZ4_LASTLITERALS) + (mc + 240) / 255 > olimit) return 0;
-      if (mc >= 15) {
-        tokval += 15;
-        mc -= 15;
-        const int nff = mc / 255;
-        warp_fill_bytes(d + op, nff, 255);
-        if (lane == 0) d[op + nff] = (u8)(mc - nff * 255);
-        op += nff + 1;
-      } else tokval += (u32)mc;
-      if (lane == 0) d[token] = (u8)tokval;
+      mc += back;
+
+      /* ---- emit (lz4.c:1112-1226) ---- */
+      const int token = op++;
+      if (!imm && limited && op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255 > olimit) return 0;
+      if (lit < 15 && mc < 15) {
+        if (limited && op + lit + 2 + (1 + LZ4_LASTLITERALS) > olimit) return 0;
+        u32 v;
+        if (lane == 0) v = ((u32)lit << 4) | (u32)mc;
+        else if (lane <= lit) v = s[anchor + lane - 1];
+        else v = lane == lit + 1 ? (u32)off : (u32)off >> 8;
+        if (lane <= lit + 2) d[token + lane] = (u8)v;
+        op += lit + 2;
+      } else {
+        u32 tokval;
+        if (lit >= 15) {
+          const int len = lit - 15, nff = len / 255;
+          tokval = 15u << 4;
+          warp_fill_bytes(d + op, nff, 255);
+          if (lane == 0) d[op + nff] = (u8)(len - nff * 255);
+          op += nff + 1;
+        } else tokval = (u32)lit << 4;
+        warp_copy_bytes(d + op, s + anchor, lit);
+        op += lit;
+        if (lane == 0) { d[op] = (u8)off; d[op + 1] = (u8)(off >> 8); }
+        op += 2;
+        if (limited && op + (1 + LZ4_LASTLITERALS) + (mc + 240) / 255 > olimit) return 0;
+        if (mc >= 15) {
+          tokval += 15;
+          const int rest = mc - 15, nff = rest / 255;
+          warp_fill_bytes(d + op, nff, 255);
+          if (lane == 0) d[op + nff] = (u8)(rest - nff * 255);
+          op += nff + 1;
+        } else tokval += (u32)mc;
+        if (lane == 0) d[token] = (u8)tokval;
+      }
 
       anchor = ip;
-      if (ip >= mfl1) { more = false; break; }                 /* lz4.c:1230-1233 */
-
-      /* fill table at ip-2, then test the next position (lz4.c:1236-1294) */
-      const u32 h2 = lz4_hash_at<U16>(s, ip - 2);
-      const u32 h = lz4_hash_at<U16>(s, ip);
-      int cand = 0;
-      if (lane == 0) {
-        LZ4_TPUT(h2, ip - 2);
-        cand = LZ4_TGET(h);
-        LZ4_TPUT(h, ip);
-      }
-      cand = __shfl_sync(FULLMASK, cand, 0);
-      __syncwarp();
-      if ((U16 || cand + 65535 >= ip) && ld_u32(s + cand) == ld_u32(s + ip)) {
-        token = op++;
-        tokval = 0;
-        match = cand;
-        continue;
-      }
-      ip++;                                                    /* lz4.c:1298 */
-      break;
+      if (ip >= mfl1) break;                                         /* lz4.c:1230-1233 */
+      post = true;
     }
   }
 
@@ -187,14 +336,64 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
 #undef LZ4_TPUT
 }
 
+/* ---- decoder ---- */
+#define LZ4D_RING 16384                      /* bytes of recent output mirrored in shared memory, per warp */
+#define LZ4D_RMASK (LZ4D_RING - 1)
+
+DEV u32 win_byte(u32 b0, u32 b1, u32 b2, int i) {             /* byte i (0..11) of a 12-byte window */
+  const u32 w = i < 4 ? b0 : (i < 8 ? b1 : b2);
+  return (w >> ((i & 3) * 8)) & 0xffu;
+}
+
 /* LZ4_decompress_safe for one stream (lz4.c:2451-2456; safe-loop rules :2234-2436).
- * Returns the number of bytes written or -1.  offset==0 is rejected. */
-DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, const int cap) {
+ * Returns the number of bytes written or -1.  offset==0 is rejected.
+ *
+ * `ring` (LZ4D_RING bytes of warp-private shared memory) mirrors the most recent output so
+ * that match sources -- a few KiB back in >99% of the sequences of shuffled data -- come
+ * from shared memory instead of a global load behind the stores that produced them.
+ * Fast path: token, literals (<= 8) and offset are parsed from one 12-byte register window,
+ * and the whole sequence (literals + match, <= 26 bytes) is produced by one predicated
+ * load/store step, one lane per output byte. */
+DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, const int cap, u8* ring_ptr) {
   const int iend = csize, oend = cap;
+  const int lane = lane_id();
+  const StreamBase ib = make_stream_base(in);
+  const smem_addr_t ring = smem_addr(ring_ptr);
   int ip = 0, op = 0;
+  int ring_lo = 0;                           /* positions [max(ring_lo, op-RING), op) are valid in the ring */
   if (cap == 0) return (csize == 1 && in[0] == 0) ? 0 : -1;   /* lz4.c:2062-2066 */
   if (csize == 0) return -1;
   for (;;) {
+    /* ---- fast path: short sequence, source strictly before this sequence's output ---- */
+    if (ip + 20 <= iend) {
+      u32 b0, b1, b2;
+      ldp_win12(ib, ip, b0, b1, b2);
+      const u32 token = b0 & 0xffu;
+      const int lit = (int)(token >> 4), mln = (int)(token & 15u);
+      if (lit <= 8 && mln != 15) {
+        const int ml = mln + 4, total = lit + ml;
+        const int ob = 1 + lit;                                /* window byte of the 16-bit offset (1..9) */
+        const u32 ow = ob < 4 ? __funnelshift_r(b0, b1, 8u * ob) : (ob < 8 ? __funnelshift_r(b1, b2, 8u * (ob - 4)) : b2 >> (8u * (ob - 8)));
+        const int off = (int)(ow & 0xffffu);
+        const int match = op + lit - off;
+        if (off >= total && op + total <= oend - LZ4_MFLIMIT) { /* no self-overlap; far from the end of the block */
+          if (match < 0) return -1;                            /* lz4.c:2356 (off == 0 cannot get here: off >= total >= 4) */
+          const bool use_ring = off <= LZ4D_RING - 64 && match >= ring_lo;
+          if (lane < total) {
+            u32 v;
+            if (lane < lit) v = in[ip + 1 + lane];
+            else if (use_ring) v = smem_ld_u8(ring, (u32)(match + lane - lit) & LZ4D_RMASK);
+            else v = out[match + lane - lit];
+            out[op + lane] = (u8)v;
+            smem_st_u8(ring, (u32)(op + lane) & LZ4D_RMASK, v);
+          }
+          __syncwarp();
+          ip += 3 + lit; op += total;
+          continue;
+        }
+      }
+    }
+    /* ---- general path ---- */
     const u32 token = in[ip++];
     int len = (int)(token >> 4);
     if (len == 15) {                                          /* read_variable_length(ip, iend-15, 1) */
@@ -208,13 +407,15 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       } while (sb == 255);
     }
     int cpy = op + len;
-    if (cpy > oend - LZ4_MFLIMIT || ip + len > iend - (2 + 1 + LZ4_LASTLITERALS)) {   /* lz4.c:2289-2331 */
-      if (ip + len != iend || cpy > oend) return -1;
-      warp_copy_bytes(out + op, in + ip, len);
-      op += len;
-      break;
+    const bool last = cpy > oend - LZ4_MFLIMIT || ip + len > iend - (2 + 1 + LZ4_LASTLITERALS);   /* lz4.c:2289-2331 */
+    if (last && (ip + len != iend || cpy > oend)) return -1;
+    for (int k = lane; k < len; k += 32) {                    /* literals -> output (+ ring) */
+      const u32 v = in[ip + k];
+      out[op + k] = (u8)v;
+      smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
     }
-    warp_copy_bytes(out + op, in + ip, len);
+    if (len > LZ4D_RING - 64) ring_lo = cpy - (LZ4D_RING - 64) > ring_lo ? cpy - (LZ4D_RING - 64) : ring_lo;
+    if (last) { op += len; break; }
     ip += len; op = cpy;
     const int off = (int)in[ip] | ((int)in[ip + 1] << 8);
     ip += 2;
@@ -234,7 +435,20 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
     cpy = op + len;
     if (cpy > oend - LZ4_LASTLITERALS) return -1;             /* lz4.c:2423 */
     __syncwarp();                                             /* earlier output must be visible to all lanes */
-    warp_copy_match(out, op, match, len);
+    if (len <= 2048 && off <= LZ4D_RING - 2048 - 64 && match >= ring_lo) {
+      /* sources are all inside the ring and are not overwritten by this copy */
+      for (int k0 = 0; k0 < len; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < len) {
+          const u32 v = smem_ld_u8(ring, (u32)(match + (off >= len ? k : k % off)) & LZ4D_RMASK);
+          out[op + k] = (u8)v;
+          smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
+        }
+      }
+    } else {
+      warp_copy_match(out, op, match, len);                   /* global sources; ring no longer mirrors this span */
+      ring_lo = cpy;
+    }
     __syncwarp();
     op = cpy;
   }

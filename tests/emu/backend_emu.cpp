@@ -89,12 +89,12 @@ int b2_launch_compact(const CompactArgs* a, b2_stream_t) {
 }
 
 int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
-  const int wpc = 4;
+  const int wpc = DECODE_WARPS;
   const int ctas = (a->map.nstreams + wpc - 1) / wpc;
   if (ctas <= 0) return 0;
   g_launches++;
   DecodeArgs args = *a;
-  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), 0, [&] { decode_kernel(args); });
+  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_RING, [&] { decode_kernel(args); });
   return 0;
 }
 
@@ -110,8 +110,8 @@ int emu_lz4_encode(const unsigned char* src, int n, unsigned char* dst, int cap,
 }
 int emu_lz4_decode(const unsigned char* src, int csize, unsigned char* dst, int cap) {
   int result = 0;
-  simt::launch(simt::Dim3(1), simt::Dim3(32), 0, [&] {
-    int r = lz4_decode_warp(src, csize, dst, cap);
+  simt::launch(simt::Dim3(1), simt::Dim3(32), LZ4D_RING, [&] {
+    int r = lz4_decode_warp(src, csize, dst, cap, simt::g_dynsmem);
     if ((threadIdx.x & 31) == 13) result = r;
   });
   return result;

@@ -37,6 +37,7 @@ typedef struct EncodeArgs {
   const uint8_t* in;     /* filtered (or original) bytes, block-major */
   uint8_t* slots;        /* per-stream output slots at the same offsets as `in` */
   int* csizes;           /* [nstreams] compressed size; == stream length means "stored raw" */
+  int* needs;            /* [nstreams] smallest `maxout` with which the codec would still have succeeded */
   int codec, clevel, accel, split_flag;
   int table_bytes;       /* shared-memory bytes per warp */
   int* queue;            /* zero-initialised work counter: warps pull stream numbers from it */
@@ -44,9 +45,12 @@ typedef struct EncodeArgs {
 
 typedef struct ScanArgs {
   const int* csizes;
+  const int* needs;
   int* bstarts;          /* [nblocks] out */
   int* result;           /* [0] = total cbytes (clamped to INT_MAX), [1] = fits */
   int nsplits, nfull, has_leftover;
+  int blocksize, leftover;
+  int serial;            /* 1: reproduce serial_blosc's per-split maxout clamp (blosc.c:646-651); 0: t_blosc's total-fit rule */
   long long destsize;
 } ScanArgs;
 

@@ -51,7 +51,7 @@ typedef struct {
 typedef struct {
   int in_use, ready, dev;
   b2_stream_t stream;
-  b2_buf in, filt, slots, out, csizes, bstarts;
+  b2_buf in, filt, slots, out, csizes, needs, bstarts;
   int* d_result;        /* [0] cbytes [1] fits [2] decode status [3] work-queue counter */
   int* h_result;        /* pinned mirror */
 } b2_ws;
@@ -121,7 +121,7 @@ int blosc_free_resources(void) {                              /* blosc.h:411 */
     b2_ws* w = &g_ws[i];
     if (w->in_use || !w->ready) continue;
     buf_free(&w->in); buf_free(&w->filt); buf_free(&w->slots); buf_free(&w->out);
-    buf_free(&w->csizes); buf_free(&w->bstarts);
+    buf_free(&w->csizes); buf_free(&w->needs); buf_free(&w->bstarts);
   }
   pthread_mutex_unlock(&g_ws_mutex);
   return 0;
@@ -386,16 +386,20 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     ea.map.nfull = nfull; ea.map.leftover = leftover; ea.map.nstreams = nfull * nsplits + (leftover ? 1 : 0);
     if (buf_ensure(&w->slots, (size_t)nb + 64)) break;
     if (buf_ensure(&w->csizes, (size_t)ea.map.nstreams * 4 + 64)) break;
+    if (buf_ensure(&w->needs, (size_t)ea.map.nstreams * 4 + 64)) break;
     if (buf_ensure(&w->bstarts, (size_t)nblocks * 4 + 64)) break;
-    ea.in = d_codec_in; ea.slots = (uint8_t*)w->slots.p; ea.csizes = (int*)w->csizes.p;
+    ea.in = d_codec_in; ea.slots = (uint8_t*)w->slots.p; ea.csizes = (int*)w->csizes.p; ea.needs = (int*)w->needs.p;
     ea.codec = compcode == BLOSC_LZ4 ? B2_CODEC_LZ4 : B2_CODEC_BLOSCLZ;
     ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
     ea.split_flag = !dont_split;
     ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
     ea.queue = w->d_result + 3;
-    if (b2_memset_dev(ea.queue, 0, 4, w->stream)) break;
+    if (b2_memset_dev(w->d_result + 2, 0, 8, w->stream)) break;          /* scan verdict scratch + work-queue counter */
     if (b2_launch_encode(&ea, w->stream)) break;
-    sa.csizes = ea.csizes; sa.bstarts = (int*)w->bstarts.p; sa.result = w->d_result;
+    sa.csizes = ea.csizes; sa.needs = ea.needs; sa.blocksize = bs; sa.leftover = leftover;
+    /* do_job runs serial_blosc when nthreads == 1 or there is at most one block (blosc.c:910) */
+    sa.serial = (numinternalthreads == 1 || nb / bs <= 1);
+    sa.bstarts = (int*)w->bstarts.p; sa.result = w->d_result;
     sa.nsplits = nsplits; sa.nfull = nfull; sa.has_leftover = leftover > 0; sa.destsize = dsz;
     if (b2_launch_scan(&sa, w->stream)) break;
     if (dest_dev) d_dest = (uint8_t*)dest;

@@ -116,7 +116,7 @@ DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
  * compressible / does not fit in maxout).  `tabmem`: (4 << hashlog) bytes, at least
  * BLZ_PROBE_TABLE_BYTES, warp-private shared memory. */
 DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int length, u8* __restrict__ out,
-                        const int maxout, const int split_block, void* tabmem) {
+                        const int maxout, const int split_block, void* tabmem, int* need_out) {
   const int lane = lane_id();
   const int maxlen = length / 4, shift = length - maxlen;
   const double cratio = blz_probe_warp(b + shift, maxlen, tabmem);          /* :425-430 */
@@ -143,6 +143,8 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
 
   const int ip_bound = length - 1, ip_limit = length - 12, op_limit = maxout;
   int ip = 4, op = 5, copy = 4;
+  int need = 66;                                                            /* :473-475: maxout < 66 is refused */
+#define BLZ_LIMIT(v) do { const int v_ = (v); if (v_ > need) need = v_; if (v_ > op_limit) return 0; } while (0)
   if (lane == 0) { out[0] = BLZ_MAX_COPY - 1; out[1] = b[0]; out[2] = b[1]; out[3] = b[2]; out[4] = b[3]; }   /* :481-487 */
 
   while (ip < ip_limit) {
@@ -150,7 +152,7 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
     const int f = blz_search_round<u32, true>(b, ip, ip_limit, tab, hashlog, ipshift, minlen, &nvalid, &cand, &m);
     const int nlit = f < 32 ? f : nvalid;
     if (nlit > 0) {                                                          /* LITERAL x nlit, :246-256 */
-      if (op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2 > op_limit) return 0;
+      BLZ_LIMIT(op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2);
       if (lane < nlit) {
         const int o = op + lane + ((copy + lane) >> 5);
         out[o] = b[ip + lane];
@@ -175,7 +177,7 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
     const bool far = distance >= BLZ_MAX_DISTANCE;
     if (far) distance -= BLZ_MAX_DISTANCE;                                   /* :559 */
     if (len < 7) {                                                           /* MATCH_SHORT[_FAR] */
-      if (op + (far ? 4 : 2) > op_limit) return 0;
+      BLZ_LIMIT(op + (far ? 4 : 2));
       if (lane == 0) {
         if (!far) { out[op] = (u8)((len << 5) + (distance >> 8)); out[op + 1] = (u8)(distance & 255); }
         else { out[op] = (u8)((len << 5) + 31); out[op + 1] = 255; out[op + 2] = (u8)(distance >> 8); out[op + 3] = (u8)(distance & 255); }
@@ -184,7 +186,7 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
     } else {                                                                 /* MATCH_LONG[_FAR] */
       len -= 7;
       const int nff = (int)(len / 255);
-      if (op + 1 + nff + (far ? 4 : 2) > op_limit) return 0;
+      BLZ_LIMIT(op + 1 + nff + (far ? 4 : 2));
       if (lane == 0) out[op] = (u8)((7u << 5) + (far ? 31u : (distance >> 8)));
       op++;
       warp_fill_bytes(out + op, nff, 255);
@@ -204,7 +206,7 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
     }
     __syncwarp();
     ip += 2;
-    if (op + 1 > op_limit) return 0;                                         /* :582-586 */
+    BLZ_LIMIT(op + 1);                                                       /* :582-586 */
     if (lane == 0) out[op] = BLZ_MAX_COPY - 1;
     op++;
   }
@@ -213,7 +215,7 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
   while (ip <= ip_bound) {
     int nlit = ip_bound - ip + 1;
     if (nlit > 32) nlit = 32;
-    if (op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2 > op_limit) return 0;
+    BLZ_LIMIT(op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2);
     if (lane < nlit) {
       const int o = op + lane + ((copy + lane) >> 5);
       out[o] = b[ip + lane];
@@ -228,7 +230,9 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
   else op--;
   __syncwarp();
   if (lane == 0) out[0] |= (1u << 5);                                        /* :607 */
+  *need_out = need;
   return op;
+#undef BLZ_LIMIT
 }
 
 /* blosclz_decompress for one stream (blosclz.c:679-789).  Returns bytes written, 0 on error. */

@@ -75,15 +75,15 @@ __global__ void encode_kernel(EncodeArgs a) {
     stream_locate(a.map, idx, &block, &off, &len, &split);
     const u8* in = a.in + off;
     u8* out = a.slots + off;
-    int c;
+    int c, need = 0;
     if (a.codec == B2_CODEC_LZ4) {
-      if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab);   /* lz4.c:710,1389 */
-      else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab);
+      if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab, &need);   /* lz4.c:710,1389 */
+      else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab, &need);
     } else {
-      c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab);
+      c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab, &need);
     }
     if (c <= 0 || c >= len) c = len;           /* blosc.c:705-714: incompressible split is stored raw */
-    if (lane_id() == 0) a.csizes[idx] = c;
+    if (lane_id() == 0) { a.csizes[idx] = c; a.needs[idx] = need; }
     __syncwarp();
   }
 }
@@ -111,15 +111,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
     __syncthreads();
   }
   long long pos = 16 + 4ll * nblocks + (tid ? part[tid - 1] : 0);
+  int bad = 0;
   for (int b = b0; b < b1; b++) {
     a.bstarts[b] = (int)(pos > 0x7fffffffll ? 0x7fffffffll : pos);
-    if (b < a.nfull) for (int s = 0; s < a.nsplits; s++) pos += 4 + (long long)a.csizes[(long long)b * a.nsplits + s];
-    else pos += 4 + (long long)a.csizes[(long long)a.nfull * a.nsplits];
+    const int ns = b < a.nfull ? a.nsplits : 1;
+    const int neblock = b < a.nfull ? a.blocksize / a.nsplits : a.leftover;
+    for (int s = 0; s < ns; s++) {
+      const long long idx = b < a.nfull ? (long long)b * a.nsplits + s : (long long)a.nfull * a.nsplits;
+      const int c = a.csizes[idx];
+      if (a.serial) {
+        /* serial_blosc hands each codec call maxout = min(neblock, room left in dest) (blosc.c:646-651):
+         * a clamped call only succeeds if the stream would have fitted that smaller budget, and a
+         * raw split needs the full neblock (blosc.c:705-711) */
+        const long long room = a.destsize - (pos + 4);
+        if (room < neblock && !(room > 0 && c < neblock && a.needs[idx] <= room)) bad = 1;
+      }
+      pos += 4 + (long long)c;
+    }
   }
+  if (bad) atomicOr(&a.result[2], 1);
+  __syncthreads();
   if (tid == SCAN_THREADS - 1) {
     const long long total = 16 + 4ll * nblocks + part[SCAN_THREADS - 1];
     a.result[0] = (int)(total > 0x7fffffffll ? 0x7fffffffll : total);
-    a.result[1] = total <= a.destsize ? 1 : 0;       /* blosc.c:1848 ntdest+cbytes > maxbytes => give up */
+    a.result[1] = (total <= a.destsize && a.result[2] == 0) ? 1 : 0;   /* blosc.c:1848 / :836-839 give up */
   }
 }
 

@@ -125,7 +125,7 @@ DEV u32 lz4_hash_seq(u32 lo, u32 b4) {                        /* lz4.c:777-806 o
  * 32-wide probe rounds only run when the first two probes miss. */
 template <bool U16>
 DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ d, const int cap,
-                        const int accel, void* tabmem) {
+                        const int accel, void* tabmem, int* need_out) {
   const int lane = lane_id();
   const StreamBase sb = make_stream_base(s);
   u16* tab16 = (u16*)tabmem;
@@ -141,6 +141,8 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   const int mfl1 = n - LZ4_MFLIMIT + 1;       /* mflimitPlusOne */
   const int matchlimit = n - LZ4_LASTLITERALS;
   int ip = 1, anchor = 0, op = 0;
+  int need = 0;                               /* max left-hand side of the limitedOutput checks = smallest capacity that passes */
+#define LZ4_LIMIT(v) do { const int v_ = (v); if (v_ > need) need = v_; if (limited && v_ > olimit) return 0; } while (0)
   /* first byte (lz4.c:1005-1010): table[hash(0)] = 0, which the zeroed table already says */
 
   if (n >= LZ4_MFLIMIT + 1) {                 /* lz4.c:1002 */
@@ -276,9 +278,9 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
 
       /* ---- emit (lz4.c:1112-1226) ---- */
       const int token = op++;
-      if (!imm && limited && op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255 > olimit) return 0;
+      if (!imm) LZ4_LIMIT(op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255);
       if (lit < 15 && mc < 15) {
-        if (limited && op + lit + 2 + (1 + LZ4_LASTLITERALS) > olimit) return 0;
+        LZ4_LIMIT(op + lit + 2 + (1 + LZ4_LASTLITERALS));
         u32 v;
         if (lane == 0) v = ((u32)lit << 4) | (u32)mc;
         else if (lane <= lit) v = s[anchor + lane - 1];
@@ -298,7 +300,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
         op += lit;
         if (lane == 0) { d[op] = (u8)off; d[op + 1] = (u8)(off >> 8); }
         op += 2;
-        if (limited && op + (1 + LZ4_LASTLITERALS) + (mc + 240) / 255 > olimit) return 0;
+        LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS) + (mc + 240) / 255);
         if (mc >= 15) {
           tokval += 15;
           const int rest = mc - 15, nff = rest / 255;
@@ -317,7 +319,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
 
   /* ---- last literals (lz4.c:1302-1329) ---- */
   const int lastRun = n - anchor;
-  if (limited && op + lastRun + 1 + (lastRun + 255 - 15) / 255 > olimit) return 0;
+  LZ4_LIMIT(op + lastRun + 1 + (lastRun + 255 - 15) / 255);
   if (lastRun >= 15) {
     const int acc = lastRun - 15, nff = acc / 255;
     if (lane == 0) d[op] = (u8)(15u << 4);
@@ -331,7 +333,9 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   }
   warp_copy_bytes(d + op, s + anchor, lastRun);
   op += lastRun;
+  *need_out = need;
   return op;
+#undef LZ4_LIMIT
 #undef LZ4_TGET
 #undef LZ4_TPUT
 }

@@ -18,11 +18,13 @@
 struct b2_stream_s { int dummy; };
 static int g_all_device = 0;
 static long long g_launches = 0;
+static int g_last_need = 0;
 
 extern "C" {
 
 void emu_set_all_device(int on) { g_all_device = on; }
 unsigned long long emu_collectives(void) { return simt::g_collectives; }
+int emu_last_need(void) { return g_last_need; }
 
 int b2_backend_init(void) { return 0; }
 int b2_get_device(void) { return 0; }
@@ -102,8 +104,10 @@ int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
 int emu_lz4_encode(const unsigned char* src, int n, unsigned char* dst, int cap, int accel) {
   int result = 0;
   simt::launch(simt::Dim3(1), simt::Dim3(32), LZ4_TABLE_BYTES, [&] {
-    int r = n < 65536 + LZ4_MFLIMIT - 1 ? lz4_encode_warp<true>(src, n, dst, cap, accel, simt::g_dynsmem)
-                                        : lz4_encode_warp<false>(src, n, dst, cap, accel, simt::g_dynsmem);
+    int need = 0;
+    int r = n < 65536 + LZ4_MFLIMIT - 1 ? lz4_encode_warp<true>(src, n, dst, cap, accel, simt::g_dynsmem, &need)
+                                        : lz4_encode_warp<false>(src, n, dst, cap, accel, simt::g_dynsmem, &need);
+    if ((threadIdx.x & 31) == 3) g_last_need = need;
     if ((threadIdx.x & 31) == 7) result = r;
   });
   return result;
@@ -119,7 +123,9 @@ int emu_lz4_decode(const unsigned char* src, int csize, unsigned char* dst, int 
 int emu_blz_encode(int clevel, const unsigned char* src, int n, unsigned char* dst, int maxout, int split) {
   int result = 0;
   simt::launch(simt::Dim3(1), simt::Dim3(32), 65536, [&] {
-    int r = blz_encode_warp(clevel, src, n, dst, maxout, split, simt::g_dynsmem);
+    int need = 0;
+    int r = blz_encode_warp(clevel, src, n, dst, maxout, split, simt::g_dynsmem, &need);
+    if ((threadIdx.x & 31) == 3) g_last_need = need;
     if ((threadIdx.x & 31) == 31) result = r;
   });
   return result;

@@ -36,7 +36,7 @@ static long long g_launches = 0;
 /* per-device one-time setup (opt-in to > 48 KiB dynamic shared memory) */
 extern "C" int b2_device_prepare(void) {
   CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_RING));
+  CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
   return 0;
 }
@@ -177,7 +177,7 @@ extern "C" int b2_launch_decode(const DecodeArgs* a, b2_stream_t s) {
   const int ctas = (a->map.nstreams + wpc - 1) / wpc;
   if (ctas <= 0) return 0;
   ProfScope ps(B2_K_DECODE, s->s);
-  decode_kernel<<<ctas, wpc * 32, (size_t)wpc * LZ4D_RING, s->s>>>(*a);
+  decode_kernel<<<ctas, wpc * 32, (size_t)wpc * LZ4D_SMEM, s->s>>>(*a);
   CK(cudaGetLastError());
   return 0;
 }

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactArgs a)
 DEV int ld_i32(const u8* p) { return (int)ld_u32(p); }
 
 #define DECODE_WARPS 4
-/* dynamic shared memory: DECODE_WARPS * LZ4D_RING bytes (per-warp ring of recent output) */
+/* dynamic shared memory: DECODE_WARPS * LZ4D_SMEM bytes (per-warp ring of recent output) */
 __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a) {
 #ifdef SIMT_EMU
   u8* smem = simt::g_dynsmem;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a)
       const u8* src = a.chunk + so;
       if (cs == len) warp_copy_bytes(out, src, len);                    /* stored raw, blosc.c:773-776 */
       else {
-        const int n = a.codec == B2_CODEC_LZ4 ? lz4_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_RING)
+        const int n = a.codec == B2_CODEC_LZ4 ? lz4_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM)
                                                : blz_decode_warp(src, cs, out, len);
         if (n != len) err = B2_ERR_CODEC;                               /* blosc.c:778-782 */
       }

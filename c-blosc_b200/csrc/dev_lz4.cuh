@@ -104,6 +104,19 @@ DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
 #endif
 }
 
+DEV void ldp_win16(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2, u32& b3) {   /* touches at most p+19 */
+#ifdef SIMT_EMU
+  memcpy(&b0, sb.s + p, 4); memcpy(&b1, sb.s + p + 4, 4); memcpy(&b2, sb.s + p + 8, 4); memcpy(&b3, sb.s + p + 12, 4);
+#else
+  const int q = p + sb.sal;
+  const u32* w = sb.s32 + (q >> 2);
+  const u32 sh = (u32)(q & 3) * 8u;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
+  b2 = __funnelshift_r(w2, w3, sh); b3 = __funnelshift_r(w3, w4, sh);
+#endif
+}
+
 template <bool U16>
 DEV u32 lz4_hash_seq(u32 lo, u32 b4) {                        /* lz4.c:777-806 on bytes already in registers */
   if (U16) return (lo * 2654435761u) >> (32 - 13);
@@ -145,6 +158,17 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
 #define LZ4_LIMIT(v) do { const int v_ = (v); if (v_ > need) need = v_; if (limited && v_ > olimit) return 0; } while (0)
   /* first byte (lz4.c:1005-1010): table[hash(0)] = 0, which the zeroed table already says */
 
+  /* Lane-cached window for the literal-free chains that dominate shuffled data: lane l keeps the
+   * 8 bytes at position w0+l and their hash, so the "fill table at ip-2 / test ip" step
+   * (lz4.c:1236-1294) fetches both hashes and the bytes to compare with shuffles instead of
+   * reloading and re-hashing; a refill costs one round of loads per ~2 sequences.  The 3-byte
+   * sequences such a chain produces (token, offset) are parked one per lane and written together. */
+  int w0 = -(1 << 30);
+  u32 wq0 = 0, wq1 = 0, wh = 0;
+  int nrec = 0, recop = 0;
+  u32 rec = 0;
+#define LZ4_FLUSH() do { if (lane < nrec) { d[recop] = (u8)rec; d[recop + 1] = (u8)(rec >> 8); d[recop + 2] = (u8)(rec >> 16); } nrec = 0; } while (0)
+
   if (n >= LZ4_MFLIMIT + 1) {                 /* lz4.c:1002 */
     bool post = false;                        /* true: a match just ended at ip (== anchor) */
     for (;;) {
@@ -152,7 +176,55 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       u32 ipn = 0, cn = 0;                    /* bytes [ip+4, ip+8) and [match+4, match+8) of the hit */
       bool have_next = false, hit = false, imm = false;
 
-      if (post) {
+      if (post && ip + 64 <= n) {
+        /* ---- chained "test next position" on the lane-cached window ---- */
+        if (ip - 2 < w0 || ip > w0 + 23) {
+          w0 = ip - 2;
+          ldp_win8(sb, w0 + lane, wq0, wq1);
+          wh = lz4_hash_seq<U16>(wq0, wq1);
+        }
+        const int li = ip - w0;                                            /* 2 .. 23 */
+        const u32 h2 = __shfl_sync(FULLMASK, wh, li - 2);
+        const u32 h = __shfl_sync(FULLMASK, wh, li);
+        const u32 seq = __shfl_sync(FULLMASK, wq0, li);
+        const u32 n4 = __shfl_sync(FULLMASK, wq1, li);                     /* bytes ip+4 .. ip+7 */
+        const u32 n8 = __shfl_sync(FULLMASK, wq0, li + 8);                 /* bytes ip+8 .. ip+11 */
+        const u32 n12 = __shfl_sync(FULLMASK, wq1, li + 8);                /* bytes ip+12 .. ip+15 */
+        LZ4_TPUT(h2, ip - 2);
+        const int cand = LZ4_TGET(h);
+        __syncwarp();
+        LZ4_TPUT(h, ip);
+        bool chained = false;
+        if (U16 || cand + 65535 >= ip) {
+          u32 c0, c1, c2, c3;
+          ldp_win16(sb, cand, c0, c1, c2, c3);
+          if (c0 == seq) {
+            int mc;
+            const u32 x1 = n4 ^ c1, x2 = n8 ^ c2, x3 = n12 ^ c3;
+            if (x1) mc = eq_bytes32(x1);
+            else if (x2) mc = 4 + eq_bytes32(x2);
+            else if (x3) mc = 8 + eq_bytes32(x3);
+            else mc = 12 + warp_count_match(s, ip + 16, cand + 16, matchlimit);   /* ip+64 <= n: far from matchlimit */
+            const int off = ip - cand;
+            if (mc < 15) {
+              LZ4_LIMIT(op + 1 + 2 + (1 + LZ4_LASTLITERALS));               /* lz4.c:1187-1211 with 0 literals */
+              if (lane == nrec) { rec = (u32)mc | ((u32)off << 8); recop = op; }
+              nrec++;
+              op += 3;
+              if (nrec == 32) LZ4_FLUSH();
+              ip += mc + 4;
+              anchor = ip;
+              if (ip >= mfl1) break;                                         /* lz4.c:1230-1233 */
+              chained = true;
+            } else {                                                         /* long match: general emission below */
+              hit = true; imm = true; match = cand;
+              ipn = n4; cn = c1; have_next = true;
+            }
+          }
+        }
+        if (chained) continue;
+        if (!hit) ip++;                                                      /* lz4.c:1298 */
+      } else if (post) {
         /* ---- fill table at ip-2, test position ip (lz4.c:1236-1294); no literals on a hit ---- */
         u32 b0, b1, b2 = 0;
         const bool wide = ip + 14 <= n;
@@ -277,6 +349,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       mc += back;
 
       /* ---- emit (lz4.c:1112-1226) ---- */
+      LZ4_FLUSH();
       const int token = op++;
       if (!imm) LZ4_LIMIT(op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255);
       if (lit < 15 && mc < 15) {
@@ -318,6 +391,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   }
 
   /* ---- last literals (lz4.c:1302-1329) ---- */
+  LZ4_FLUSH();
   const int lastRun = n - anchor;
   LZ4_LIMIT(op + lastRun + 1 + (lastRun + 255 - 15) / 255);
   if (lastRun >= 15) {
@@ -335,14 +409,26 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   op += lastRun;
   *need_out = need;
   return op;
+#undef LZ4_FLUSH
 #undef LZ4_LIMIT
 #undef LZ4_TGET
 #undef LZ4_TPUT
 }
 
 /* ---- decoder ---- */
+#ifdef SIMT_EMU
+static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d_general_seqs = 0;
+#define LZ4D_DBG(x) do { if (lane == 0) (x)++; } while (0)
+#define LZ4D_DBGN(x, n) do { if (lane == 0) (x) += (n); } while (0)
+#else
+#define LZ4D_DBG(x) do {} while (0)
+#define LZ4D_DBGN(x, n) do {} while (0)
+#endif
 #define LZ4D_RING 16384                      /* bytes of recent output mirrored in shared memory, per warp */
 #define LZ4D_RMASK (LZ4D_RING - 1)
+#define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 26) */
+#define LZ4D_SCRATCH 256                     /* per-warp shared scratch after the ring: sequence table + start-bit words */
+#define LZ4D_SMEM (LZ4D_RING + LZ4D_SCRATCH)
 
 DEV u32 win_byte(u32 b0, u32 b1, u32 b2, int i) {             /* byte i (0..11) of a 12-byte window */
   const u32 w = i < 4 ? b0 : (i < 8 ? b1 : b2);
@@ -364,11 +450,97 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
   const StreamBase ib = make_stream_base(in);
   const smem_addr_t ring = smem_addr(ring_ptr);
   int ip = 0, op = 0;
+  if (lane < 10) ((u32*)(ring_ptr + LZ4D_RING))[24 + lane] = 0;
+  __syncwarp();
   int ring_lo = 0;                           /* positions [max(ring_lo, op-RING), op) are valid in the ring */
   if (cap == 0) return (csize == 1 && in[0] == 0) ? 0 : -1;   /* lz4.c:2062-2066 */
   if (csize == 0) return -1;
   for (;;) {
-    /* ---- fast path: short sequence, source strictly before this sequence's output ---- */
+    /* ---- batch path: up to 11 short sequences per round ----
+     * Lane l speculates that a sequence starts at input byte ip+l and parses it from its own
+     * 12-byte window.  Sequences whose offset reaches back past everything this batch can write
+     * (>= LZ4D_BATCH_OUT) cannot depend on each other, so once the chain of real starts is known
+     * (one ballot when every sequence is the 3-byte literal-free form, a shuffle walk otherwise)
+     * all their output bytes are produced 32 per instruction. */
+    if (ip + 48 <= iend && op + LZ4D_BATCH_OUT <= oend - LZ4_MFLIMIT) {
+      u32 b0, b1, b2;
+      ldp_win12(ib, ip + lane, b0, b1, b2);
+      const u32 token = b0 & 0xffu;
+      const int lit = (int)(token >> 4), mln = (int)(token & 15u);
+      const int ob = 1 + lit;                                  /* window byte of the 16-bit offset (valid for lit <= 8) */
+      const u32 ow = ob < 4 ? __funnelshift_r(b0, b1, 8u * ob) : (ob < 8 ? __funnelshift_r(b1, b2, 8u * (ob - 4)) : b2 >> (8u * ((ob - 8) & 3)));
+      const int off = (int)(ow & 0xffffu);
+      const int L = 3 + lit, O = lit + mln + 4;
+      const bool good = lit <= 8 && mln != 15 && off >= LZ4D_BATCH_OUT;
+      int nseq = 0, consumed = 0, total = 0, my_rank = -1, my_opre = 0;
+      const unsigned g3 = __ballot_sync(FULLMASK, good && lit == 0);
+      if ((g3 & 0x49249249u) == 0x49249249u) {                 /* starts at lanes 0,3,...,30 */
+        const bool real = (lane % 3) == 0;
+        const int v = real ? O : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(FULLMASK, incl, d);
+          if (lane >= d) incl += t;
+        }
+        if (real) { my_rank = lane / 3; my_opre = incl - v; }
+        nseq = 11; consumed = 33;
+        total = __shfl_sync(FULLMASK, incl, 31);
+      } else {
+        const u32 packed = (good ? 1u : 0u) | ((u32)L << 1) | ((u32)O << 5);
+        int cur = 0;
+        while (cur < 32) {
+          const u32 pk = __shfl_sync(FULLMASK, packed, cur);
+          if (!(pk & 1u)) break;
+          if (lane == cur) { my_rank = nseq; my_opre = total; }
+          total += (int)((pk >> 5) & 31u);
+          cur += (int)((pk >> 1) & 15u);
+          nseq++;
+        }
+        consumed = cur;
+      }
+      if (nseq > 0) {
+        const int match = op + my_opre + lit - off;            /* meaningful on real lanes */
+        if (__ballot_sync(FULLMASK, my_rank >= 0 && match < 0)) return -1;   /* lz4.c:2356 */
+        u32* tbl = (u32*)(ring_ptr + LZ4D_RING);               /* 11 x {info, off} then 10 start-bit words */
+        u32* smask = tbl + 24;
+        if (my_rank >= 0) {
+          tbl[2 * my_rank] = (u32)my_opre | ((u32)lit << 9) | ((u32)lane << 13);
+          tbl[2 * my_rank + 1] = (u32)off;
+          atomicOr(&smask[my_opre >> 5], 1u << (my_opre & 31));
+        }
+        __syncwarp();
+        int kbase = 0;
+        for (int r = 0; r * 32 < total; r++) {
+          const u32 w = smask[r];
+          const int y = r * 32 + lane;
+          if (y < total) {
+            const int k = kbase + __popc(w & ((2u << lane) - 1u)) - 1;
+            const u32 e0 = tbl[2 * k], offk = tbl[2 * k + 1];
+            const int opre = (int)(e0 & 511u), litk = (int)((e0 >> 9) & 15u), lanek = (int)(e0 >> 13);
+            const int j = y - opre;
+            u32 v;
+            if (j < litk) v = in[ip + lanek + 1 + j];
+            else {
+              const int src = op + opre + litk - (int)offk + (j - litk);
+              const int m0 = op + opre + litk - (int)offk;
+              if ((int)offk <= LZ4D_RING - LZ4D_BATCH_OUT - 64 && m0 >= ring_lo) v = smem_ld_u8(ring, (u32)src & LZ4D_RMASK);
+              else v = out[src];
+            }
+            out[op + y] = (u8)v;
+            smem_st_u8(ring, (u32)(op + y) & LZ4D_RMASK, v);
+          }
+          kbase += __popc(w);
+        }
+        __syncwarp();
+        if (lane < 10) smask[lane] = 0;
+        __syncwarp();
+        ip += consumed; op += total;
+        LZ4D_DBGN(g_dbg_lz4d_batch_seqs, nseq);
+        continue;
+      }
+    }
+    /* ---- single-sequence fast path: short sequence, source strictly before its own output ---- */
     if (ip + 20 <= iend) {
       u32 b0, b1, b2;
       ldp_win12(ib, ip, b0, b1, b2);
@@ -376,7 +548,7 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       const int lit = (int)(token >> 4), mln = (int)(token & 15u);
       if (lit <= 8 && mln != 15) {
         const int ml = mln + 4, total = lit + ml;
-        const int ob = 1 + lit;                                /* window byte of the 16-bit offset (1..9) */
+        const int ob = 1 + lit;
         const u32 ow = ob < 4 ? __funnelshift_r(b0, b1, 8u * ob) : (ob < 8 ? __funnelshift_r(b1, b2, 8u * (ob - 4)) : b2 >> (8u * (ob - 8)));
         const int off = (int)(ow & 0xffffu);
         const int match = op + lit - off;
@@ -393,11 +565,13 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
           }
           __syncwarp();
           ip += 3 + lit; op += total;
+          LZ4D_DBG(g_dbg_lz4d_fast_seqs);
           continue;
         }
       }
     }
     /* ---- general path ---- */
+    LZ4D_DBG(g_dbg_lz4d_general_seqs);
     const u32 token = in[ip++];
     int len = (int)(token >> 4);
     if (len == 15) {                                          /* read_variable_length(ip, iend-15, 1) */

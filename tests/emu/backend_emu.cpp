@@ -25,6 +25,7 @@ extern "C" {
 void emu_set_all_device(int on) { g_all_device = on; }
 unsigned long long emu_collectives(void) { return simt::g_collectives; }
 int emu_last_need(void) { return g_last_need; }
+void emu_lz4d_counters(long long* c) { c[0] = g_dbg_lz4d_batch_seqs; c[1] = g_dbg_lz4d_fast_seqs; c[2] = g_dbg_lz4d_general_seqs; }
 
 int b2_backend_init(void) { return 0; }
 int b2_get_device(void) { return 0; }
@@ -96,7 +97,7 @@ int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
   if (ctas <= 0) return 0;
   g_launches++;
   DecodeArgs args = *a;
-  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_RING, [&] { decode_kernel(args); });
+  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_SMEM, [&] { decode_kernel(args); });
   return 0;
 }
 
@@ -114,7 +115,7 @@ int emu_lz4_encode(const unsigned char* src, int n, unsigned char* dst, int cap,
 }
 int emu_lz4_decode(const unsigned char* src, int csize, unsigned char* dst, int cap) {
   int result = 0;
-  simt::launch(simt::Dim3(1), simt::Dim3(32), LZ4D_RING, [&] {
+  simt::launch(simt::Dim3(1), simt::Dim3(32), LZ4D_SMEM, [&] {
     int r = lz4_decode_warp(src, csize, dst, cap, simt::g_dynsmem);
     if ((threadIdx.x & 31) == 13) result = r;
   });

@@ -88,7 +88,7 @@ DEV void ldp_win12(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2) {
   const int q = p + sb.sal;
   const u32* w = sb.s32 + (q >> 2);
   const u32 sh = (u32)(q & 3) * 8u;
-  const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+  const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
 #endif
 }
@@ -99,7 +99,7 @@ DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
   const int q = p + sb.sal;
   const u32* w = sb.s32 + (q >> 2);
   const u32 sh = (u32)(q & 3) * 8u;
-  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+  const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
 #endif
 }
@@ -111,7 +111,7 @@ DEV void ldp_win16(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2, u32& 
   const int q = p + sb.sal;
   const u32* w = sb.s32 + (q >> 2);
   const u32 sh = (u32)(q & 3) * 8u;
-  const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+  const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
   b2 = __funnelshift_r(w2, w3, sh); b3 = __funnelshift_r(w3, w4, sh);
 #endif
@@ -204,7 +204,15 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
             if (x1) mc = eq_bytes32(x1);
             else if (x2) mc = 4 + eq_bytes32(x2);
             else if (x3) mc = 8 + eq_bytes32(x3);
-            else mc = 12 + warp_count_match(s, ip + 16, cand + 16, matchlimit);   /* ip+64 <= n: far from matchlimit */
+            else {                                                            /* 16-byte matches are common: one more word */
+              u32 p4, p5, q4, q5;
+              ldp_win8(sb, ip + 16, p4, p5);
+              ldp_win8(sb, cand + 16, q4, q5);
+              const u32 x4 = p4 ^ q4, x5 = p5 ^ q5;
+              if (x4) mc = 12 + eq_bytes32(x4);
+              else if (x5) mc = 16 + eq_bytes32(x5);
+              else mc = 20 + warp_count_match(s, ip + 24, cand + 24, matchlimit);   /* ip+64 <= n: far from matchlimit */
+            }
             const int off = ip - cand;
             if (mc < 15) {
               LZ4_LIMIT(op + 1 + 2 + (1 + LZ4_LASTLITERALS));               /* lz4.c:1187-1211 with 0 literals */

@@ -78,6 +78,31 @@ DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, TabT* t
   return f;
 }
 
+/* The same step for ONE position, warp-uniform (all lanes compute the same values and do the
+ * same table store): used right after a match, where the next position very often matches
+ * again (chains of short matches dominate shuffled data) and a 32-wide round would be wasted. */
+template <typename TabT, bool FARRULE>
+DEV int blz_probe_one(const u8* __restrict__ b, int pos, TabT* tab, u32 hashlog, int ipshift, int minlen,
+                      int* cand_f, int* m_f) {
+  const u32 seq = ld_u32(b + pos);
+  const u32 h = blz_hash(seq, hashlog);
+  const int cand = (int)tab[h];
+  __syncwarp();                              /* all lanes have read the old entry */
+  if (lane_id() == 0) tab[h] = (TabT)pos;
+  __syncwarp();                              /* ordered before lane 0's later inserts and everybody's next lookups */
+  const u32 dist = (u32)(pos - cand);
+  if (dist == 0 || dist >= BLZ_MAX_FARDISTANCE || ld_u32(b + cand) != seq) return 32;
+  int m;
+  const u32 x1 = ld_u32(b + pos + 4) ^ ld_u32(b + cand + 4);
+  if (x1) m = 4 + eq_bytes32(x1);
+  else m = 8 + eq_bytes32(ld_u32(b + pos + 8) ^ ld_u32(b + cand + 8));
+  const int len = m + 1 - ipshift;
+  const bool far = FARRULE && (dist - 1u >= BLZ_MAX_DISTANCE);
+  if (!(m >= 12 || (len >= minlen && !(len <= 5 && far)))) return 32;
+  *cand_f = cand; *m_f = m;
+  return 0;
+}
+
 /* get_cratio (blosclz.c:318-418) on the probe window b[0..maxlen).  `tabmem` is
  * BLZ_PROBE_TABLE_BYTES of warp-private shared memory. */
 DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
@@ -147,9 +172,12 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
 #define BLZ_LIMIT(v) do { const int v_ = (v); if (v_ > need) need = v_; if (v_ > op_limit) return 0; } while (0)
   if (lane == 0) { out[0] = BLZ_MAX_COPY - 1; out[1] = b[0]; out[2] = b[1]; out[3] = b[2]; out[4] = b[3]; }   /* :481-487 */
 
+  bool post = false;                                                         /* a match was just emitted */
   while (ip < ip_limit) {
-    int nvalid, cand, m;
-    const int f = blz_search_round<u32, true>(b, ip, ip_limit, tab, hashlog, ipshift, minlen, &nvalid, &cand, &m);
+    int nvalid = 1, cand = 0, m = 0, f;
+    if (post) f = blz_probe_one<u32, true>(b, ip, tab, hashlog, ipshift, minlen, &cand, &m);
+    else f = blz_search_round<u32, true>(b, ip, ip_limit, tab, hashlog, ipshift, minlen, &nvalid, &cand, &m);
+    post = f < 32;
     const int nlit = f < 32 ? f : nvalid;
     if (nlit > 0) {                                                          /* LITERAL x nlit, :246-256 */
       BLZ_LIMIT(op + (nlit - 1) + ((copy + nlit - 1) >> 5) + 2);

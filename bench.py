@@ -41,6 +41,20 @@ def bench_words(nbytes, np):
     return w.view(np.uint8)
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one encode_kernel launch, from the committed
+    `ncu --set full` summary (profiles/); None when no capture exists for this workload."""
+    name = {"lz4-shuffle-ts4-cl5-256MiB": "r1_ncu_lz4_cfg2_v5.json"}.get(workload)
+    p = os.path.join(ROOT, "profiles", name) if name else None
+    if p and os.path.exists(p):
+        try:
+            d = json.load(open(p))["encode_kernel"]
+            return int((d["dram__bytes_read.sum"]["value"] + d["dram__bytes_write.sum"]["value"]) * 1e6)
+        except Exception:
+            return None
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -272,6 +286,30 @@ def main():
     ms_h, tc_h, td_h, cb_h, nb_h = timed(host_args, args.steps)
     assert cb_h == cb and nb_h == nbytes and torch.equal(out_h, src_h)
 
+    # supplementary: 4 independent chunks in flight from 4 host threads (the _ctx API is re-entrant; the
+    # codec kernels are latency-bound per stream, so independent chunks overlap on the GPU)
+    conc = None
+    if world == 1:
+        K = 4
+        bufs = [(d_src.clone(), torch.zeros_like(d_chunk), torch.zeros_like(d_out)) for _ in range(K)]
+
+        def worker(i):
+            s_, c_, o_ = bufs[i]
+            pkg.compress_ctx(clevel, shuf, ts, nbytes, s_, c_, nbytes + 16, comp_name)
+            pkg.decompress_ctx(c_, o_, nbytes)
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=worker, args=(i,)) for i in range(K)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        assert all(torch.equal(b[2], d_src) for b in bufs)
+        conc = {"chunks_in_flight": K, "value": K * 2 * nbytes / dt / 1e9, "unit": "GB/s",
+                "note": "4 x (compress+decompress) of 256 MiB issued concurrently from 4 host threads, device resident"}
+        del bufs
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,11 +335,13 @@ def main():
                     "compress_gbs": world * nbytes / (tc_h / args.steps) / 1e9, "decompress_gbs": world * nbytes / (td_h / args.steps) / 1e9},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "encode_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                         "frac": achieved / hbm, "traffic": ncu_traffic(args.workload), "peak_source": hbm_src,
                          "algorithmic_bytes_per_launch": nbytes + cb, "avg_launch_ms": enc_avg * 1e3,
                          "decode_kernel": {"achieved": (nbytes + cb) / (dec_ms / max(dec_n, 1) / 1e3) / 1e9 if dec_ms else 0.0,
                                            "avg_launch_ms": dec_ms / max(dec_n, 1)}},
             "kernels": kernels}
+    if conc:
+        line["concurrent"] = conc
     if cpu:
         t = cpu["tc"] + cpu["td"]
         line["cpu_baseline"] = {"value": 2 * nbytes / t / 1e9, "unit": "GB/s", "cores": cpu["cores"], "kind": cpu["kind"],

@@ -393,6 +393,8 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
     ea.split_flag = !dont_split;
     ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
+    /* BloscLZ at clevel >= 3: 17-bit packed table (34 KiB instead of 64 KiB) when every stream is <= 128 KiB */
+    if (ea.codec == B2_CODEC_BLOSCLZ && clevel >= 3 && bs / nsplits <= 131072 && leftover <= 131072) ea.table_bytes = 32768 + 2048;
     ea.queue = w->d_result + 3;
     if (b2_memset_dev(w->d_result + 2, 0, 8, w->stream)) break;          /* scan verdict scratch + work-queue counter */
     if (b2_launch_encode(&ea, w->stream)) break;

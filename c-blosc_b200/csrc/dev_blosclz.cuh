@@ -22,6 +22,33 @@
 #define BLZ_MAX_FARDISTANCE (65535 + 8191 - 1)     /* blosclz.c:44 */
 #define BLZ_PROBE_TABLE_BYTES 8192                 /* 2^12 x u16, blosclz.c:321-322 */
 
+/* Hash-table layouts.  blosclz_compress uses 2^hashlog x u32 (64 KiB at clevel >= 3), which would
+ * limit a B200 SM to three resident streams.  For streams of at most 128 KiB (every split Blosc
+ * produces with its default block sizes) positions fit in 17 bits: 16 low bits in a u16 array plus
+ * one bit in a bitmap = 34 KiB, i.e. six streams per SM.  Same contents, same replacement policy. */
+struct BlzTab32 {
+  u32* t;
+  DEV int get(u32 h) const { return (int)t[h]; }
+  DEV void put(u32 h, int pos) const { t[h] = (u32)pos; }
+};
+struct BlzTab16 {                              /* the entropy probe's 2^12 x u16 table (blosclz.c:321-322) */
+  u16* t;
+  DEV int get(u32 h) const { return (int)t[h]; }
+  DEV void put(u32 h, int pos) const { t[h] = (u16)pos; }
+};
+struct BlzTab17 {
+  u16* lo;
+  u32* hi;
+  DEV int get(u32 h) const { return (int)lo[h] | (int)(((hi[h >> 5] >> (h & 31u)) & 1u) << 16); }
+  DEV void put(u32 h, int pos) const {
+    lo[h] = (u16)pos;
+    const u32 m = 1u << (h & 31u);
+    if (pos & 0x10000) atomicOr(&hi[h >> 5], m); else atomicAnd(&hi[h >> 5], ~m);
+  }
+};
+#define BLZ_TAB17_BYTES (32768 + 2048)
+#define BLZ_TAB17_MAXLEN 131072
+
 DEV u32 blz_hash(u32 seq, u32 hashlog) { return (seq * 2654435761u) >> (32u - hashlog); }   /* blosclz.c:58-60 */
 
 /* min(p+1, bound) with p the first position >= start where b[p] != b[p-dist]
@@ -35,8 +62,8 @@ DEV int blz_match_end_warp(const u8* __restrict__ b, int start, int dist, int bo
  * ip .. ip+31 (those < ip_limit).  Returns the first accepting lane (32 if none),
  * the number of valid lanes in *nvalid, and for the accepting lane its candidate and
  * its capped match length (4..12) in *cand_f / *m_f.  Commits table entries. */
-template <typename TabT, bool FARRULE>
-DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, TabT* tab, u32 hashlog,
+template <typename Tab, bool FARRULE>
+DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, const Tab tab, u32 hashlog,
                          int ipshift, int minlen, int* nvalid, int* cand_f, int* m_f) {
   const int lane = lane_id();
   const int pos = ip + lane;
@@ -49,7 +76,7 @@ DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, TabT* t
   int cand = 0, m = 0;
   bool acc = false;
   if (valid) {
-    cand = lower ? ip + (31 - __clz((int)lower)) : (int)tab[h];
+    cand = lower ? ip + (31 - __clz((int)lower)) : tab.get(h);
     const u32 dist = (u32)(pos - cand);                                    /* blosclz.c:501 */
     if (dist != 0 && dist < BLZ_MAX_FARDISTANCE && ld_u32(b + cand) == seq) {   /* :506,:512 */
       const u32 x1 = ld_u32(b + pos + 4) ^ ld_u32(b + cand + 4);
@@ -67,7 +94,7 @@ DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, TabT* t
   const int last = f < nv - 1 ? f : nv - 1;
   if (valid && lane <= last) {
     const unsigned le = last >= 31 ? FULLMASK : ((1u << (last + 1)) - 1u);
-    if ((((peers & le) >> lane) >> 1) == 0) tab[h] = (TabT)pos;           /* :504, last writer per hash */
+    if ((((peers & le) >> lane) >> 1) == 0) tab.put(h, pos);              /* :504, last writer per hash */
   }
   __syncwarp();
   *nvalid = nv;
@@ -81,14 +108,14 @@ DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, TabT* t
 /* The same step for ONE position, warp-uniform (all lanes compute the same values and do the
  * same table store): used right after a match, where the next position very often matches
  * again (chains of short matches dominate shuffled data) and a 32-wide round would be wasted. */
-template <typename TabT, bool FARRULE>
-DEV int blz_probe_one(const u8* __restrict__ b, int pos, TabT* tab, u32 hashlog, int ipshift, int minlen,
+template <typename Tab, bool FARRULE>
+DEV int blz_probe_one(const u8* __restrict__ b, int pos, const Tab tab, u32 hashlog, int ipshift, int minlen,
                       int* cand_f, int* m_f) {
   const u32 seq = ld_u32(b + pos);
   const u32 h = blz_hash(seq, hashlog);
-  const int cand = (int)tab[h];
+  const int cand = tab.get(h);
   __syncwarp();                              /* all lanes have read the old entry */
-  if (lane_id() == 0) tab[h] = (TabT)pos;
+  if (lane_id() == 0) tab.put(h, pos);
   __syncwarp();                              /* ordered before lane 0's later inserts and everybody's next lookups */
   const u32 dist = (u32)(pos - cand);
   if (dist == 0 || dist >= BLZ_MAX_FARDISTANCE || ld_u32(b + cand) != seq) return 32;
@@ -107,7 +134,8 @@ DEV int blz_probe_one(const u8* __restrict__ b, int pos, TabT* tab, u32 hashlog,
  * BLZ_PROBE_TABLE_BYTES of warp-private shared memory. */
 DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
   const int lane = lane_id();
-  u16* tab = (u16*)tabmem;
+  BlzTab16 tab;
+  tab.t = (u16*)tabmem;
   for (int i = lane; i < BLZ_PROBE_TABLE_BYTES / 4; i += 32) ((u32*)tabmem)[i] = 0;
   __syncwarp();
   const int limit = maxlen > 4096 ? 4096 : maxlen;
@@ -115,7 +143,7 @@ DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
   int ip = 0, oc = 5, copy = 4;
   while (ip < ip_limit) {
     int nvalid, cand, m;
-    const int f = blz_search_round<u16, false>(b, ip, ip_limit, tab, 12, 3, 3, &nvalid, &cand, &m);
+    const int f = blz_search_round<BlzTab16, false>(b, ip, ip_limit, tab, 12, 3, 3, &nvalid, &cand, &m);
     const int nlit = f < 32 ? f : nvalid;
     oc += nlit + ((copy + nlit) >> 5);                       /* LITERAL2, :258-266 */
     copy = (copy + nlit) & 31;
@@ -129,7 +157,7 @@ DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
     copy = 0;
     if (len >= 7) oc += (len - 7) / 255 + 1;
     oc += (dist - 1 < BLZ_MAX_DISTANCE) ? 2 : 4;
-    if (lane == 0) tab[blz_hash(ld_u32(b + ip), 12)] = (u16)ip;   /* :407-411 */
+    if (lane == 0) tab.put(blz_hash(ld_u32(b + ip), 12), ip);     /* :407-411 */
     __syncwarp();
     ip += 2;
     oc++;
@@ -140,8 +168,13 @@ DEV double blz_probe_warp(const u8* __restrict__ b, int maxlen, void* tabmem) {
 /* blosclz_compress for one stream.  Returns the compressed size or 0 (not
  * compressible / does not fit in maxout).  `tabmem`: (4 << hashlog) bytes, at least
  * BLZ_PROBE_TABLE_BYTES, warp-private shared memory. */
+template <typename Tab>
+DEV int blz_encode_main(const int clevel, const u8* __restrict__ b, const int length, u8* __restrict__ out,
+                        const int maxout, const int ipshift, const int minlen, const u32 hashlog, const Tab tab,
+                        int* need_out);
+
 DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int length, u8* __restrict__ out,
-                        const int maxout, const int split_block, void* tabmem, int* need_out) {
+                        const int maxout, const int split_block, void* tabmem, int table_bytes, int* need_out) {
   const int lane = lane_id();
   const int maxlen = length / 4, shift = length - maxlen;
   const double cratio = blz_probe_warp(b + shift, maxlen, tabmem);          /* :425-430 */
@@ -161,11 +194,27 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
   const u32 hashlog = clevel == 1 ? 12u : (clevel == 2 ? 13u : 14u);         /* :459-461 */
   if (length < 16 || maxout < 66) return 0;                                  /* :473-475 */
 
-  u32* tab = (u32*)tabmem;
   __syncwarp();
-  for (int i = lane; i < (1 << hashlog); i += 32) tab[i] = 0;
+  if (hashlog == 14 && table_bytes < 65536) {                               /* packed 17-bit table (host guarantees length <= 128 KiB) */
+    for (int i = lane; i < BLZ_TAB17_BYTES / 4; i += 32) ((u32*)tabmem)[i] = 0;
+    __syncwarp();
+    BlzTab17 t;
+    t.lo = (u16*)tabmem;
+    t.hi = (u32*)((u8*)tabmem + 32768);
+    return blz_encode_main<BlzTab17>(clevel, b, length, out, maxout, ipshift, minlen, hashlog, t, need_out);
+  }
+  for (int i = lane; i < (1 << hashlog); i += 32) ((u32*)tabmem)[i] = 0;
   __syncwarp();
+  BlzTab32 t;
+  t.t = (u32*)tabmem;
+  return blz_encode_main<BlzTab32>(clevel, b, length, out, maxout, ipshift, minlen, hashlog, t, need_out);
+}
 
+template <typename Tab>
+DEV int blz_encode_main(const int clevel, const u8* __restrict__ b, const int length, u8* __restrict__ out,
+                        const int maxout, const int ipshift, const int minlen, const u32 hashlog, const Tab tab,
+                        int* need_out) {
+  const int lane = lane_id();
   const int ip_bound = length - 1, ip_limit = length - 12, op_limit = maxout;
   int ip = 4, op = 5, copy = 4;
   int need = 66;                                                            /* :473-475: maxout < 66 is refused */
@@ -175,8 +224,8 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
   bool post = false;                                                         /* a match was just emitted */
   while (ip < ip_limit) {
     int nvalid = 1, cand = 0, m = 0, f;
-    if (post) f = blz_probe_one<u32, true>(b, ip, tab, hashlog, ipshift, minlen, &cand, &m);
-    else f = blz_search_round<u32, true>(b, ip, ip_limit, tab, hashlog, ipshift, minlen, &nvalid, &cand, &m);
+    if (post) f = blz_probe_one<Tab, true>(b, ip, tab, hashlog, ipshift, minlen, &cand, &m);
+    else f = blz_search_round<Tab, true>(b, ip, ip_limit, tab, hashlog, ipshift, minlen, &nvalid, &cand, &m);
     post = f < 32;
     const int nlit = f < 32 ? f : nvalid;
     if (nlit > 0) {                                                          /* LITERAL x nlit, :246-256 */
@@ -229,8 +278,8 @@ DEV int blz_encode_warp(const int clevel, const u8* __restrict__ b, const int le
     /* update the hash at match boundary (:567-580) */
     u32 seq = ld_u32(b + ip);
     if (lane == 0) {
-      tab[blz_hash(seq, hashlog)] = (u32)ip;
-      if (clevel == 9) { seq >>= 8; tab[blz_hash(seq, hashlog)] = (u32)(ip + 1); }
+      tab.put(blz_hash(seq, hashlog), ip);
+      if (clevel == 9) { seq >>= 8; tab.put(blz_hash(seq, hashlog), ip + 1); }
     }
     __syncwarp();
     ip += 2;

@@ -80,7 +80,7 @@ __global__ void encode_kernel(EncodeArgs a) {
       if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab, &need);   /* lz4.c:710,1389 */
       else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab, &need);
     } else {
-      c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab, &need);
+      c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab, a.table_bytes, &need);
     }
     if (c <= 0 || c >= len) c = len;           /* blosc.c:705-714: incompressible split is stored raw */
     if (lane_id() == 0) { a.csizes[idx] = c; a.needs[idx] = need; }

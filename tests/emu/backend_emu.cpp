@@ -19,12 +19,14 @@ struct b2_stream_s { int dummy; };
 static int g_all_device = 0;
 static long long g_launches = 0;
 static int g_last_need = 0;
+static int g_blz_pack = 1;
 
 extern "C" {
 
 void emu_set_all_device(int on) { g_all_device = on; }
 unsigned long long emu_collectives(void) { return simt::g_collectives; }
 int emu_last_need(void) { return g_last_need; }
+void emu_set_blz_pack(int on) { g_blz_pack = on; }
 void emu_lz4d_counters(long long* c) { c[0] = g_dbg_lz4d_batch_seqs; c[1] = g_dbg_lz4d_fast_seqs; c[2] = g_dbg_lz4d_general_seqs; }
 
 int b2_backend_init(void) { return 0; }
@@ -125,7 +127,7 @@ int emu_blz_encode(int clevel, const unsigned char* src, int n, unsigned char* d
   int result = 0;
   simt::launch(simt::Dim3(1), simt::Dim3(32), 65536, [&] {
     int need = 0;
-    int r = blz_encode_warp(clevel, src, n, dst, maxout, split, simt::g_dynsmem, &need);
+    int r = blz_encode_warp(clevel, src, n, dst, maxout, split, simt::g_dynsmem, (n <= BLZ_TAB17_MAXLEN && g_blz_pack) ? BLZ_TAB17_BYTES : 65536, &need);
     if ((threadIdx.x & 31) == 3) g_last_need = need;
     if ((threadIdx.x & 31) == 31) result = r;
   });

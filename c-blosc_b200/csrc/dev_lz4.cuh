@@ -167,6 +167,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   u32 wq0 = 0, wq1 = 0, wh = 0;
   int nrec = 0, recop = 0;
   u32 rec = 0;
+#define LZ4_FLUSH_CHECKED() do { if (nrec) { LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS)); } LZ4_FLUSH(); } while (0)
 #define LZ4_FLUSH() do { if (lane < nrec) { d[recop] = (u8)rec; d[recop + 1] = (u8)(rec >> 8); d[recop + 2] = (u8)(rec >> 16); } nrec = 0; } while (0)
 
   if (n >= LZ4_MFLIMIT + 1) {                 /* lz4.c:1002 */
@@ -189,37 +190,36 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
         const u32 seq = __shfl_sync(FULLMASK, wq0, li);
         const u32 n4 = __shfl_sync(FULLMASK, wq1, li);                     /* bytes ip+4 .. ip+7 */
         const u32 n8 = __shfl_sync(FULLMASK, wq0, li + 8);                 /* bytes ip+8 .. ip+11 */
-        const u32 n12 = __shfl_sync(FULLMASK, wq1, li + 8);                /* bytes ip+12 .. ip+15 */
         LZ4_TPUT(h2, ip - 2);
         const int cand = LZ4_TGET(h);
         __syncwarp();
         LZ4_TPUT(h, ip);
         bool chained = false;
         if (U16 || cand + 65535 >= ip) {
-          u32 c0, c1, c2, c3;
-          ldp_win16(sb, cand, c0, c1, c2, c3);
+          u32 c0, c1, c2;
+          ldp_win12(sb, cand, c0, c1, c2);
           if (c0 == seq) {
             int mc;
-            const u32 x1 = n4 ^ c1, x2 = n8 ^ c2, x3 = n12 ^ c3;
+            const u32 x1 = n4 ^ c1, x2 = n8 ^ c2;
             if (x1) mc = eq_bytes32(x1);
             else if (x2) mc = 4 + eq_bytes32(x2);
-            else if (x3) mc = 8 + eq_bytes32(x3);
-            else {                                                            /* 16-byte matches are common: one more word */
-              u32 p4, p5, q4, q5;
-              ldp_win8(sb, ip + 16, p4, p5);
-              ldp_win8(sb, cand + 16, q4, q5);
-              const u32 x4 = p4 ^ q4, x5 = p5 ^ q5;
-              if (x4) mc = 12 + eq_bytes32(x4);
-              else if (x5) mc = 16 + eq_bytes32(x5);
-              else mc = 20 + warp_count_match(s, ip + 24, cand + 24, matchlimit);   /* ip+64 <= n: far from matchlimit */
+            else {                                                            /* >= 12 bytes: next 8 from memory */
+              u32 p3, p4, q3, q4;
+              ldp_win8(sb, ip + 12, p3, p4);
+              ldp_win8(sb, cand + 12, q3, q4);
+              const u32 x3 = p3 ^ q3, x4 = p4 ^ q4;
+              if (x3) mc = 8 + eq_bytes32(x3);
+              else if (x4) mc = 12 + eq_bytes32(x4);
+              else mc = 16 + warp_count_match(s, ip + 20, cand + 20, matchlimit);   /* ip+64 <= n: far from matchlimit */
             }
             const int off = ip - cand;
             if (mc < 15) {
-              LZ4_LIMIT(op + 1 + 2 + (1 + LZ4_LASTLITERALS));               /* lz4.c:1187-1211 with 0 literals */
+              /* lz4.c:1187-1211 with 0 literals asks for op + 9 <= olimit; op only grows inside a chain,
+               * so the check is made once per parked batch, before anything is written (LZ4_FLUSH_CHECKED) */
               if (lane == nrec) { rec = (u32)mc | ((u32)off << 8); recop = op; }
               nrec++;
               op += 3;
-              if (nrec == 32) LZ4_FLUSH();
+              if (nrec == 32) LZ4_FLUSH_CHECKED();
               ip += mc + 4;
               anchor = ip;
               if (ip >= mfl1) break;                                         /* lz4.c:1230-1233 */
@@ -357,7 +357,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       mc += back;
 
       /* ---- emit (lz4.c:1112-1226) ---- */
-      LZ4_FLUSH();
+      LZ4_FLUSH_CHECKED();
       const int token = op++;
       if (!imm) LZ4_LIMIT(op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255);
       if (lit < 15 && mc < 15) {
@@ -399,7 +399,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   }
 
   /* ---- last literals (lz4.c:1302-1329) ---- */
-  LZ4_FLUSH();
+  LZ4_FLUSH_CHECKED();
   const int lastRun = n - anchor;
   LZ4_LIMIT(op + lastRun + 1 + (lastRun + 255 - 15) / 255);
   if (lastRun >= 15) {
@@ -417,6 +417,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   op += lastRun;
   *need_out = need;
   return op;
+#undef LZ4_FLUSH_CHECKED
 #undef LZ4_FLUSH
 #undef LZ4_LIMIT
 #undef LZ4_TGET

@@ -146,3 +146,19 @@ def test_library_error_codes(emu):
     assert decompress(emu, "blosc_decompress_ctx", chunk, n - 1)[0] == -1
     c = chunk.copy(); c[20:24] = 0xff
     assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -1
+
+
+def test_lz4_decoder_paths_are_all_exercised(emu, orc):
+    """The batch-parallel, single-sequence and general decode paths must all run (and agree with
+    the source) on shuffled bench.c data -- guards against a fast path silently never being taken."""
+    import ctypes as C
+    counters = (C.c_longlong * 3)()
+    src = gen("bench", 1 << 20)
+    cb, chunk = compress(orc, "orc_compress_ctx", 5, 1, 4, src, len(src) + 16, "lz4")
+    emu.emu_lz4d_counters(counters)
+    before = list(counters)
+    dn, out = decompress(emu, "blosc_decompress_ctx", chunk, len(src))
+    emu.emu_lz4d_counters(counters)
+    batch, fast, general = (counters[i] - before[i] for i in range(3))
+    assert dn == len(src) and (out[:dn] == src).all()
+    assert batch > 10000 and fast > 0 and general > 0, (batch, fast, general)

@@ -92,6 +92,7 @@ DEV int blz_search_round(const u8* __restrict__ b, int ip, int ip_limit, const T
   const int nv = __popc(vmask);
   const int f = found ? __ffs((int)found) - 1 : 32;
   const int last = f < nv - 1 ? f : nv - 1;
+  __syncwarp();                              /* all lookups done before any commit */
   if (valid && lane <= last) {
     const unsigned le = last >= 31 ? FULLMASK : ((1u << (last + 1)) - 1u);
     if ((((peers & le) >> lane) >> 1) == 0) tab.put(h, pos);              /* :504, last writer per hash */

@@ -190,10 +190,11 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
         const u32 seq = __shfl_sync(FULLMASK, wq0, li);
         const u32 n4 = __shfl_sync(FULLMASK, wq1, li);                     /* bytes ip+4 .. ip+7 */
         const u32 n8 = __shfl_sync(FULLMASK, wq0, li + 8);                 /* bytes ip+8 .. ip+11 */
-        LZ4_TPUT(h2, ip - 2);
-        const int cand = LZ4_TGET(h);
+        if (lane == 0) LZ4_TPUT(h2, ip - 2);
         __syncwarp();
-        LZ4_TPUT(h, ip);
+        const int cand = LZ4_TGET(h);
+        __syncwarp();                      /* every lane has read the old entry before lane 0 overwrites it */
+        if (lane == 0) LZ4_TPUT(h, ip);
         bool chained = false;
         if (U16 || cand + 65535 >= ip) {
           u32 c0, c1, c2;
@@ -241,10 +242,11 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
         const u32 seq = __funnelshift_r(b0, b1, 16);                       /* bytes ip .. ip+3 */
         const u32 h2 = lz4_hash_seq<U16>(b0, b1);                          /* 5th byte of ip-2 is s[ip+2] */
         const u32 h = lz4_hash_seq<U16>(seq, b1 >> 16);                    /* 5th byte of ip is s[ip+4] */
-        LZ4_TPUT(h2, ip - 2);
+        if (lane == 0) LZ4_TPUT(h2, ip - 2);
+        __syncwarp();
         const int cand = LZ4_TGET(h);
-        __syncwarp();                      /* every lane has read the old entry before any lane overwrites it */
-        LZ4_TPUT(h, ip);
+        __syncwarp();                      /* every lane has read the old entry before lane 0 overwrites it */
+        if (lane == 0) LZ4_TPUT(h, ip);
         if (U16 || cand + 65535 >= ip) {
           u32 c0, c1;
           ldp_win8(sb, cand, c0, c1);
@@ -267,9 +269,10 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
           if (wide) ldp_win12(sb, pos, b0, b1, b2);
           else { b0 = ld_u32(s + pos); b1 = (u32)s[pos + 4]; }
           const u32 h = lz4_hash_seq<U16>(b0, b1);
+          __syncwarp();                    /* table writes of the previous step are visible */
           const int cand = LZ4_TGET(h);
           __syncwarp();
-          LZ4_TPUT(h, pos);
+          if (lane == 0) LZ4_TPUT(h, pos);
           if (U16 || cand + 65535 >= pos) {
             u32 c0, c1;
             ldp_win8(sb, cand, c0, c1);
@@ -281,6 +284,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
           }
         }
         if (!hit && !ended) {
+          __syncwarp();
           for (int base_it = 2;; base_it += 32) {
             const int itl = base_it + lane;
             const bool valid = ip + lz4_probe_offset(itl + 1, accel) <= mfl1;
@@ -300,6 +304,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
             const int nvalid = __popc(vmask);                       /* valid lanes form a prefix */
             const int f = found ? __ffs((int)found) - 1 : 32;
             const int last = f < nvalid - 1 ? f : nvalid - 1;       /* last probe committed to the table */
+            __syncwarp();                                           /* all lookups done before any commit */
             if (valid && lane <= last) {
               const unsigned le = last >= 31 ? FULLMASK : ((1u << (last + 1)) - 1u);
               if ((((peers & le) >> lane) >> 1) == 0) LZ4_TPUT(h, pos);  /* highest committed lane per hash wins */

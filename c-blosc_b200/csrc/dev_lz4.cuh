@@ -12,8 +12,13 @@
  * lane wins, and only probes up to and including it are committed to the table, so
  * the table evolves exactly as in the serial code and the output is byte-identical.
  *
- * Decoder: LZ4_decompress_safe semantics (lz4.c:2022-2445) with warp-wide literal
- * and (period-replicating) match copies.
+ * Decoder: LZ4_decompress_safe semantics (lz4.c:2022-2445).  Three tiers: a batch path
+ * (every lane speculatively parses the sequence that would start at its input byte; the
+ * chain of real starts is resolved with one ballot or a short shuffle walk and up to 11
+ * sequences are copied 32 output bytes per instruction), a single-sequence fast path, and
+ * the general path with warp-wide literal and period-replicating match copies.  A per-warp
+ * shared-memory ring mirrors the last 16 KiB of output so match sources do not wait
+ * behind the global stores that produced them.
  */
 #pragma once
 #include "dev_common.cuh"
@@ -38,34 +43,6 @@ DEV long long lz4_probe_offset(int it, int accel) {
   return 1 + m * accel + 32 * c * (c - 1) + c * (m - 64 * c);
 }
 
-/* 12 consecutive bytes starting at q (any alignment) as three little-endian words.
- * GPU: four aligned word loads + funnel shifts; it may touch the aligned words around
- * [q, q+12), i.e. up to q+15 -- callers guarantee q+16 <= end of the stream. */
-DEV void ld_win12(const u8* q, u32& b0, u32& b1, u32& b2) {
-#ifdef SIMT_EMU
-  memcpy(&b0, q, 4); memcpy(&b1, q + 4, 4); memcpy(&b2, q + 8, 4);
-#else
-  const uintptr_t a = (uintptr_t)q;
-  const u32* w = (const u32*)(a & ~(uintptr_t)3);
-  const u32 sh = (u32)(a & 3u) * 8u;
-  const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
-#endif
-}
-
-/* 8 consecutive bytes at q; touches at most q+11 */
-DEV void ld_win8(const u8* q, u32& b0, u32& b1) {
-#ifdef SIMT_EMU
-  memcpy(&b0, q, 4); memcpy(&b1, q + 4, 4);
-#else
-  const uintptr_t a = (uintptr_t)q;
-  const u32* w = (const u32*)(a & ~(uintptr_t)3);
-  const u32 sh = (u32)(a & 3u) * 8u;
-  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
-  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
-#endif
-}
-
 /* Position-based window loads: the stream base is split once into an aligned word pointer
  * (s32) and a byte phase (sal); a window at byte position p then costs one 64-bit address
  * computation (IMAD.WIDE) instead of one per word. */
@@ -81,6 +58,9 @@ DEV StreamBase make_stream_base(const u8* s) {
   b.sal = (int)((uintptr_t)s & 3u);
   return b;
 }
+/* 12 bytes at position p as three little-endian words.  GPU: four aligned read-only word loads
+ * + funnel shifts; touches the aligned words around [p, p+12), i.e. at most byte p+15 --
+ * callers guarantee p+16 <= end of the stream (the emulator build reads exactly 12 bytes). */
 DEV void ldp_win12(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2) {
 #ifdef SIMT_EMU
   memcpy(&b0, sb.s + p, 4); memcpy(&b1, sb.s + p + 4, 4); memcpy(&b2, sb.s + p + 8, 4);
@@ -92,6 +72,7 @@ DEV void ldp_win12(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2) {
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
 #endif
 }
+/* 8 bytes at position p; touches at most byte p+11 */
 DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
 #ifdef SIMT_EMU
   memcpy(&b0, sb.s + p, 4); memcpy(&b1, sb.s + p + 4, 4);
@@ -101,19 +82,6 @@ DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
   const u32 sh = (u32)(q & 3) * 8u;
   const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
-#endif
-}
-
-DEV void ldp_win16(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2, u32& b3) {   /* touches at most p+19 */
-#ifdef SIMT_EMU
-  memcpy(&b0, sb.s + p, 4); memcpy(&b1, sb.s + p + 4, 4); memcpy(&b2, sb.s + p + 8, 4); memcpy(&b3, sb.s + p + 12, 4);
-#else
-  const int q = p + sb.sal;
-  const u32* w = sb.s32 + (q >> 2);
-  const u32 sh = (u32)(q & 3) * 8u;
-  const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
-  b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
-  b2 = __funnelshift_r(w2, w3, sh); b3 = __funnelshift_r(w3, w4, sh);
 #endif
 }
 
@@ -443,11 +411,6 @@ static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d
 #define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 26) */
 #define LZ4D_SCRATCH 256                     /* per-warp shared scratch after the ring: sequence table + start-bit words */
 #define LZ4D_SMEM (LZ4D_RING + LZ4D_SCRATCH)
-
-DEV u32 win_byte(u32 b0, u32 b1, u32 b2, int i) {             /* byte i (0..11) of a 12-byte window */
-  const u32 w = i < 4 ? b0 : (i < 8 ? b1 : b2);
-  return (w >> ((i & 3) * 8)) & 0xffu;
-}
 
 /* LZ4_decompress_safe for one stream (lz4.c:2451-2456; safe-loop rules :2234-2436).
  * Returns the number of bytes written or -1.  offset==0 is rejected.

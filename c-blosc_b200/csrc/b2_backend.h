@@ -29,6 +29,13 @@ void b2_dev_free(void* p);
 int  b2_pinned_alloc(void** p, size_t n);           /* host memory the device can DMA from/to */
 void b2_pinned_free(void* p);
 int  b2_ptr_is_device(const void* p);               /* 1 device/managed, 0 host */
+int  b2_ptr_is_pinned(const void* p);               /* 1 page-locked / registered host memory */
+
+typedef struct b2_event_s* b2_event_t;
+int  b2_event_create(b2_event_t* e);
+void b2_event_destroy(b2_event_t e);
+int  b2_event_record(b2_event_t e, b2_stream_t s);
+int  b2_event_sync(b2_event_t e);
 
 int  b2_copy_h2d(void* d, const void* h, size_t n, b2_stream_t s);
 int  b2_copy_d2h(void* h, const void* d, size_t n, b2_stream_t s);

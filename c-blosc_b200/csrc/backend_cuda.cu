@@ -76,6 +76,24 @@ extern "C" int b2_ptr_is_device(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+extern "C" int b2_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (p == NULL) return 0;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+struct b2_event_s { cudaEvent_t e; };
+extern "C" int b2_event_create(b2_event_t* e) {
+  b2_event_s* ev = new b2_event_s;
+  if (cudaEventCreateWithFlags(&ev->e, cudaEventDisableTiming) != cudaSuccess) { delete ev; return -1; }
+  *e = ev;
+  return 0;
+}
+extern "C" void b2_event_destroy(b2_event_t e) { if (e) { cudaEventDestroy(e->e); delete e; } }
+extern "C" int b2_event_record(b2_event_t e, b2_stream_t s) { CK(cudaEventRecord(e->e, s->s)); return 0; }
+extern "C" int b2_event_sync(b2_event_t e) { CK(cudaEventSynchronize(e->e)); return 0; }
+
 extern "C" int b2_copy_h2d(void* d, const void* h, size_t n, b2_stream_t s) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s->s)); return 0; }
 extern "C" int b2_copy_d2h(void* h, const void* d, size_t n, b2_stream_t s) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s->s)); return 0; }
 extern "C" int b2_copy_d2d(void* d, const void* s_, size_t n, b2_stream_t s) { CK(cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s->s)); return 0; }

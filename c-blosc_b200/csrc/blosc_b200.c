@@ -41,6 +41,85 @@ static void wr_i32(uint8_t* p, int32_t v) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* pageable-host staging: a small pool of copy threads + pinned bounce slices */
+/* ------------------------------------------------------------------------- */
+/* Callers of the C API usually hand in malloc'ed (pageable) buffers.  cudaMemcpy from pageable
+ * memory runs at a fraction of the PCIe rate, so such buffers go through page-locked bounce
+ * slices instead: a few host threads copy slice i+1 while the DMA engine moves slice i. */
+#define B2_STAGE_SLICE ((size_t)8 << 20)
+#define B2_STAGE_DEPTH 4
+#define B2_COPY_THREADS_MAX 16
+
+typedef struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv_work, cv_done;
+  int nthreads, started, generation, pending, stop;
+  uint8_t* dst;
+  const uint8_t* src;
+  size_t len;
+  pthread_t th[B2_COPY_THREADS_MAX];
+  int ids[B2_COPY_THREADS_MAX];
+} b2_copy_pool;
+
+static b2_copy_pool g_cp = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, 0, 0, 0, NULL, NULL, 0, {0}, {0}};
+static pthread_mutex_t g_cp_user = PTHREAD_MUTEX_INITIALIZER;      /* one parallel copy at a time */
+
+static void* copy_worker(void* arg) {
+  const int id = *(int*)arg;
+  int seen = 0;
+  pthread_mutex_lock(&g_cp.mu);
+  for (;;) {
+    while (!g_cp.stop && g_cp.generation == seen) pthread_cond_wait(&g_cp.cv_work, &g_cp.mu);
+    if (g_cp.stop) break;
+    seen = g_cp.generation;
+    {
+      const size_t per = ((g_cp.len + g_cp.nthreads - 1) / g_cp.nthreads + 63) & ~(size_t)63;
+      const size_t lo = per * (size_t)id, hi = lo + per < g_cp.len ? lo + per : g_cp.len;
+      uint8_t* d = g_cp.dst;
+      const uint8_t* s = g_cp.src;
+      pthread_mutex_unlock(&g_cp.mu);
+      if (lo < hi) memcpy(d + lo, s + lo, hi - lo);
+      pthread_mutex_lock(&g_cp.mu);
+    }
+    if (--g_cp.pending == 0) pthread_cond_signal(&g_cp.cv_done);
+  }
+  pthread_mutex_unlock(&g_cp.mu);
+  return NULL;
+}
+
+static void parallel_memcpy(void* dst, const void* src, size_t len) {
+  int i;
+  if (len < ((size_t)1 << 20)) { memcpy(dst, src, len); return; }
+  pthread_mutex_lock(&g_cp_user);
+  pthread_mutex_lock(&g_cp.mu);
+  if (!g_cp.started) {
+    const char* e = getenv("BLOSC_B200_COPY_THREADS");
+    int n = e ? atoi(e) : 8;
+    if (n < 1) n = 1;
+    if (n > B2_COPY_THREADS_MAX) n = B2_COPY_THREADS_MAX;
+    g_cp.nthreads = 0;
+    for (i = 0; i < n; i++) {
+      g_cp.ids[i] = i;
+      if (pthread_create(&g_cp.th[i], NULL, copy_worker, &g_cp.ids[i]) != 0) break;
+      g_cp.nthreads++;
+    }
+    g_cp.started = 1;
+  }
+  if (g_cp.nthreads == 0) {
+    pthread_mutex_unlock(&g_cp.mu);
+    memcpy(dst, src, len);
+  } else {
+    g_cp.dst = (uint8_t*)dst; g_cp.src = (const uint8_t*)src; g_cp.len = len;
+    g_cp.pending = g_cp.nthreads;
+    g_cp.generation++;
+    pthread_cond_broadcast(&g_cp.cv_work);
+    while (g_cp.pending) pthread_cond_wait(&g_cp.cv_done, &g_cp.mu);
+    pthread_mutex_unlock(&g_cp.mu);
+  }
+  pthread_mutex_unlock(&g_cp_user);
+}
+
+/* ------------------------------------------------------------------------- */
 /* workspace pool: device scratch + one stream per concurrent call            */
 /* ------------------------------------------------------------------------- */
 typedef struct {
@@ -54,6 +133,8 @@ typedef struct {
   b2_buf in, filt, slots, out, csizes, needs, bstarts;
   int* d_result;        /* [0] cbytes [1] fits [2] decode status [3] work-queue counter */
   int* h_result;        /* pinned mirror */
+  uint8_t* stage[B2_STAGE_DEPTH];   /* pinned bounce slices for pageable host buffers (lazy) */
+  b2_event_t stage_ev[B2_STAGE_DEPTH];
 } b2_ws;
 
 #define B2_MAX_WS 16
@@ -283,6 +364,61 @@ static int copy_any(void* dst, int dst_dev, const void* src, int src_dev, size_t
   return rc;
 }
 
+static int stage_ready(b2_ws* w) {
+  int k;
+  if (w->stage[0]) return 0;
+  for (k = 0; k < B2_STAGE_DEPTH; k++) {
+    void* p = NULL;
+    if (b2_pinned_alloc(&p, B2_STAGE_SLICE) || b2_event_create(&w->stage_ev[k])) return -1;
+    w->stage[k] = (uint8_t*)p;
+  }
+  return 0;
+}
+
+/* host -> device; pageable sources go through the bounce slices */
+static int h2d_any(b2_ws* w, void* dst, const void* src, size_t n) {
+  size_t off;
+  int i = 0;
+  if (n == 0) return 0;
+  if (n < B2_STAGE_SLICE / 4 || b2_ptr_is_pinned(src) || stage_ready(w)) return b2_copy_h2d(dst, src, n, w->stream);
+  for (off = 0; off < n; off += B2_STAGE_SLICE, i++) {
+    const int k = i % B2_STAGE_DEPTH;
+    const size_t len = n - off < B2_STAGE_SLICE ? n - off : B2_STAGE_SLICE;
+    if (i >= B2_STAGE_DEPTH && b2_event_sync(w->stage_ev[k])) return -1;     /* slice k's previous DMA has drained */
+    parallel_memcpy(w->stage[k], (const uint8_t*)src + off, len);
+    if (b2_copy_h2d((uint8_t*)dst + off, w->stage[k], len, w->stream)) return -1;
+    if (b2_event_record(w->stage_ev[k], w->stream)) return -1;
+  }
+  return 0;
+}
+
+/* device -> host, completes before returning; pageable destinations go through the bounce slices */
+static int d2h_any(b2_ws* w, void* dst, const void* src, size_t n) {
+  size_t off;
+  int i = 0, nsl;
+  if (n == 0) return 0;
+  if (n < B2_STAGE_SLICE / 4 || b2_ptr_is_pinned(dst) || stage_ready(w)) {
+    if (b2_copy_d2h(dst, src, n, w->stream)) return -1;
+    return b2_stream_sync(w->stream);
+  }
+  nsl = (int)((n + B2_STAGE_SLICE - 1) / B2_STAGE_SLICE);
+  for (i = 0; i < nsl + B2_STAGE_DEPTH - 1; i++) {
+    if (i < nsl) {                                   /* issue the DMA of slice i */
+      const int k = i % B2_STAGE_DEPTH;
+      off = (size_t)i * B2_STAGE_SLICE;
+      if (b2_copy_d2h(w->stage[k], (const uint8_t*)src + off, n - off < B2_STAGE_SLICE ? n - off : B2_STAGE_SLICE, w->stream)) return -1;
+      if (b2_event_record(w->stage_ev[k], w->stream)) return -1;
+    }
+    if (i >= B2_STAGE_DEPTH - 1) {                   /* drain slice j = i - (DEPTH-1) to the caller's buffer */
+      const int j = i - (B2_STAGE_DEPTH - 1), k = j % B2_STAGE_DEPTH;
+      off = (size_t)j * B2_STAGE_SLICE;
+      if (b2_event_sync(w->stage_ev[k])) return -1;
+      parallel_memcpy((uint8_t*)dst + off, w->stage[k], n - off < B2_STAGE_SLICE ? n - off : B2_STAGE_SLICE);
+    }
+  }
+  return 0;
+}
+
 static void make_header(uint8_t* h, int versionlz, int flags, int typesize, int32_t nbytes, int32_t blocksize,
                         int32_t cbytes) {                                  /* blosc.c:1154-1215,1275 */
   h[0] = BLOSC_VERSION_FORMAT; h[1] = (uint8_t)versionlz; h[2] = (uint8_t)flags; h[3] = (uint8_t)typesize;
@@ -366,7 +502,7 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     if (src_dev) d_src = (const uint8_t*)src;
     else {
       if (buf_ensure(&w->in, (size_t)nb + 64)) break;
-      if (b2_copy_h2d(w->in.p, src, (size_t)nb, w->stream)) break;
+      if (h2d_any(w, w->in.p, src, (size_t)nb)) break;
       d_src = (const uint8_t*)w->in.p;
     }
     /* filter (blosc.c:607-622): byte shuffle needs typesize > 1; bitshuffle applies per block when bsize >= typesize */
@@ -416,8 +552,7 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     if (w->h_result[1]) {                                                 /* fits */
       const int32_t cbytes = w->h_result[0];
       if (!dest_dev) {
-        if (b2_copy_d2h(dest, d_dest, (size_t)cbytes, w->stream)) break;
-        if (b2_stream_sync(w->stream)) break;
+        if (d2h_any(w, dest, d_dest, (size_t)cbytes)) break;
       }
       result = cbytes;
     } else if (nb + BLOSC_MAX_OVERHEAD <= dsz) {                          /* blosc.c:1264-1272 */
@@ -547,7 +682,7 @@ int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numin
     if (src_dev) d_chunk = (const uint8_t*)src;
     else {
       if (buf_ensure(&w->in, (size_t)h.cbytes + 64)) break;
-      if (b2_copy_h2d(w->in.p, src, (size_t)h.cbytes, w->stream)) break;
+      if (h2d_any(w, w->in.p, src, (size_t)h.cbytes)) break;
       d_chunk = (const uint8_t*)w->in.p;
     }
     if (dest_dev) d_out = (uint8_t*)dest;
@@ -555,8 +690,7 @@ int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numin
     rc = decode_blocks(w, &h, codec, d_chunk, 0, h.nblocks, d_out);
     if (rc < 0) { result = -1; break; }                                    /* blosc.c:1511-1514 */
     if (!dest_dev) {
-      if (b2_copy_d2h(dest, d_out, (size_t)h.nbytes, w->stream)) break;
-      if (b2_stream_sync(w->stream)) break;
+      if (d2h_any(w, dest, d_out, (size_t)h.nbytes)) break;
     }
     result = h.nbytes;
   } while (0);
@@ -616,7 +750,7 @@ int blosc_getitem(const void* src, int start, int nitems, void* dest) {    /* bl
     if (src_dev) d_chunk = (const uint8_t*)src;
     else {
       if (buf_ensure(&w->in, (size_t)h.cbytes + 64)) break;
-      if (b2_copy_h2d(w->in.p, src, (size_t)h.cbytes, w->stream)) break;
+      if (h2d_any(w, w->in.p, src, (size_t)h.cbytes)) break;
       d_chunk = (const uint8_t*)w->in.p;
     }
     if (buf_ensure(&w->out, (size_t)count * (size_t)h.blocksize + 64)) break;

@@ -41,6 +41,14 @@ void b2_dev_free(void* p) { free(p); }
 int b2_pinned_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : -1; }
 void b2_pinned_free(void* p) { free(p); }
 int b2_ptr_is_device(const void*) { return g_all_device; }
+static int g_all_pinned = 1;
+void emu_set_all_pinned(int on) { g_all_pinned = on; }
+int b2_ptr_is_pinned(const void*) { return g_all_pinned; }
+struct b2_event_s { int dummy; };
+int b2_event_create(b2_event_t* e) { *e = new b2_event_s; return 0; }
+void b2_event_destroy(b2_event_t e) { delete e; }
+int b2_event_record(b2_event_t, b2_stream_t) { return 0; }
+int b2_event_sync(b2_event_t) { return 0; }
 int b2_copy_h2d(void* d, const void* h, size_t n, b2_stream_t) { memcpy(d, h, n); return 0; }
 int b2_copy_d2h(void* h, const void* d, size_t n, b2_stream_t) { memcpy(h, d, n); return 0; }
 int b2_copy_d2d(void* d, const void* s, size_t n, b2_stream_t) { memmove(d, s, n); return 0; }

@@ -162,3 +162,23 @@ def test_lz4_decoder_paths_are_all_exercised(emu, orc):
     batch, fast, general = (counters[i] - before[i] for i in range(3))
     assert dn == len(src) and (out[:dn] == src).all()
     assert batch > 10000 and fast > 0 and general > 0, (batch, fast, general)
+
+
+def test_pageable_host_staging(emu, orc):
+    """Host buffers that are not page-locked go through the pinned bounce slices filled by the copy
+    thread pool (blosc_b200.c h2d_any / d2h_any): multi-slice pipeline in both directions."""
+    emu.emu_set_all_pinned(0)
+    try:
+        n = (20 << 20) + 4321                     # > 2 bounce slices each way
+        src = gen("bench", n)
+        cb, chunk = compress(emu, "blosc_compress_ctx", 5, 1, 4, src, n + 16, "lz4")
+        assert cb > 0
+        dn, out = decompress(emu, "blosc_decompress_ctx", chunk, n)
+        assert dn == n and (out[:n] == src).all()
+        rnd = gen("rand", 12 << 20)               # MEMCPYED fallback: the compressed side is large too
+        cb, chunk = compress(emu, "blosc_compress_ctx", 5, 1, 4, rnd, len(rnd) + 16, "blosclz")
+        assert cb == len(rnd) + 16
+        dn, out = decompress(emu, "blosc_decompress_ctx", chunk, len(rnd))
+        assert dn == len(rnd) and (out[:dn] == rnd).all()
+    finally:
+        emu.emu_set_all_pinned(1)

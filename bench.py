@@ -31,6 +31,12 @@ WORKLOADS = {
     "lz4-shuffle-ts4-cl5-256MiB": ("lz4", 1, 4, 5, 256 << 20),
     "blosclz-bitshuffle-ts8-cl5-256MiB": ("blosclz", 2, 8, 5, 256 << 20),
 }
+# BASELINE.json configs[4]: 8 GiB = 32 independent 256 MiB chunks sharded over the GPUs of one box
+# (32/N chunks per rank), typesize sweep; opt-in with --workload
+SHARDED = {
+    # name: (compressor, doshuffle, clevel, total bytes, chunk bytes, typesizes, headline typesize)
+    "lz4-shuffle-cl5-8GiB-sharded": ("lz4", 1, 5, 8 << 30, 256 << 20, (1, 2, 4, 8, 16), 4),
+}
 DEFAULT_WORKLOAD = "lz4-shuffle-ts4-cl5-256MiB"
 METRIC = "compress+decompress GB/s"
 
@@ -162,13 +168,214 @@ def cpu_roundtrip(np, workload, nthreads, repeats):
     return {"kind": kind, "cores": nthreads, "tc": tc / repeats, "td": td / repeats, "cbytes": cb, "nbytes": nbytes}
 
 
+def cpu_chunks(np, comp_name, shuf, ts, clevel, chunk_bytes, nchunks, nthreads):
+    """Reference CPU implementation over `nchunks` independent chunks, one after another, each with
+    the reference's own pool of `nthreads` threads (how bench.c drives it)."""
+    kind, comp, dec = load_ref()
+    if kind == "port":
+        nthreads = 1
+    src = bench_words(chunk_bytes, np).copy()
+    chunk = np.zeros(chunk_bytes + 16, np.uint8)
+    out = np.zeros(chunk_bytes, np.uint8)
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+
+    def once():
+        t0 = time.perf_counter()
+        cb = comp(ci(clevel), ci(shuf), sz(ts), sz(chunk_bytes), src.ctypes.data_as(vp), chunk.ctypes.data_as(vp),
+                  sz(chunk_bytes + 16), comp_name.encode(), sz(0), ci(nthreads))
+        t1 = time.perf_counter()
+        nb = dec(chunk.ctypes.data_as(vp), out.ctypes.data_as(vp), sz(chunk_bytes), ci(nthreads))
+        assert cb > 0 and nb == chunk_bytes
+        return t1 - t0, time.perf_counter() - t1, cb
+    t_w = time.perf_counter()
+    n = 0
+    while n < 3 or time.perf_counter() - t_w < 2.0:
+        once(); n += 1
+    tc = td = 0.0
+    for _ in range(nchunks):
+        a, b, cb = once()
+        tc += a; td += b
+    return {"kind": kind, "cores": nthreads, "tc": tc, "td": td, "cbytes": cb, "bytes": nchunks * chunk_bytes}
+
+
+def run_sharded(args, np, rank, world, local_rank):
+    """8 GiB as 32 chunks of 256 MiB, 32/N per GPU, each rank's run compressed as one frame
+    (blosc_b200_frame_*: 4 chunks in flight per GPU).  No collective inside the algorithm; a
+    second leg adds the scatter of input slices from rank 0 and the gather-v of the compressed
+    frames over NCCL (c-blosc_b200/sharding.py)."""
+    comp_name, shuf, clevel, total, chunk, sweep, head_ts = SHARDED[args.workload]
+    nchunks = total // chunk
+    assert nchunks % world == 0, "32 chunks must divide over the ranks"
+    k = nchunks // world
+    mine = k * chunk
+    host_threads = args.cpu_threads or min(len(os.sched_getaffinity(0)) or 1, 256)
+    config = {"workload": args.workload, "codec": comp_name, "filter": "shuffle", "typesize": head_ts, "typesizes": list(sweep),
+              "clevel": clevel, "total_bytes": total, "chunk_bytes": chunk, "chunks_per_gpu": k,
+              "sharding": "whole chunks per GPU (contiguous runs), no data-path collective; per-chunk restart of the bench.c generator",
+              "l2": "inputs (>= 1 GiB per GPU) larger than the 126 MB L2, no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = 4
+        r = cpu_chunks(np, comp_name, shuf, head_ts, clevel, chunk, sample, host_threads)
+        t = r["tc"] + r["td"]
+        val = 2 * r["bytes"] / t / 1e9
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": t * 1e3 * nchunks / sample, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                          "compress_gbs": r["bytes"] / r["tc"] / 1e9, "decompress_gbs": r["bytes"] / r["td"] / 1e9,
+                          "ratio": chunk / r["cbytes"],
+                          "cpu_baseline": {"value": val, "unit": "GB/s", "cores": r["cores"], "kind": r["kind"],
+                                           "sample": f"{sample} of the {nchunks} chunks, one after another, nthreads={r['cores']} each"},
+                          "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+
+    if world > 1:
+        os.environ["CUDA_VISIBLE_DEVICES"] = os.environ.get("CUDA_VISIBLE_DEVICES", ",".join(str(i) for i in range(world))).split(",")[local_rank]
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from cblosc_b200 import sharding
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", 0 if world > 1 else local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    one_h = torch.from_numpy(bench_words(chunk, np).copy())
+    d_src = one_h.to(dev).repeat(k)
+    bound = pkg.frame_bound(mine, 1, chunk)
+    d_frame = torch.empty(bound, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(mine, dtype=torch.uint8, device=dev)
+
+    def timed(ts, src, frame, out, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        tc = td = 0.0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fb = pkg.frame_compress(clevel, shuf, ts, mine, src, frame, bound, comp_name, 0, chunk)
+            t1 = time.perf_counter()
+            nb = pkg.frame_decompress(frame, fb, out, mine)
+            tc += t1 - t0; td += time.perf_counter() - t1
+            assert fb > 0 and nb == mine
+        e1.record()
+        torch.cuda.synchronize()
+        ms, tc, td = reduce_max([e0.elapsed_time(e1), tc, td])
+        barrier()
+        return ms, tc, td, fb
+
+    sampler = ClockSampler(local_rank if world > 1 else torch.cuda.current_device())
+    sweep_out = {}
+    launches0 = None
+    head = None
+    for ts in sweep:
+        timed(ts, d_src, d_frame, d_out, max(1, min(args.warmup, 2)))
+        assert torch.equal(d_out, d_src), f"round trip mismatch at typesize {ts}"
+        if ts == head_ts:
+            pkg.set_profiling(True); pkg.prof_reset(); launches0 = pkg.launch_count(); sampler.start()
+        ms, tc, td, fb = timed(ts, d_src, d_frame, d_out, args.steps)
+        if ts == head_ts:
+            clocks = sampler.stop(); launches = pkg.launch_count() - launches0; prof = pkg.prof_get(); pkg.set_profiling(False)
+            head = (ms, tc, td, fb)
+        cb_chunk = (fb - 32 - 8 * k) // k
+        sweep_out[str(ts)] = {"value": 2 * total / (ms / args.steps / 1e3) / 1e9, "compress_gbs": total / (tc / args.steps) / 1e9,
+                              "decompress_gbs": total / (td / args.steps) / 1e9, "ratio": chunk / cb_chunk, "cbytes_per_chunk": cb_chunk}
+
+    # end to end for the headline typesize: pinned host slice -> frame in pinned host memory -> pinned host output
+    src_h = one_h.repeat(k).pin_memory()
+    frame_h = torch.empty(bound, dtype=torch.uint8).pin_memory()
+    out_h = torch.empty(mine, dtype=torch.uint8).pin_memory()
+    timed(head_ts, src_h, frame_h, out_h, 1)
+    assert torch.equal(out_h, src_h), "host round trip mismatch"
+    ms_h, tc_h, td_h, fb_h = timed(head_ts, src_h, frame_h, out_h, args.steps)
+    assert fb_h == head[3]
+    del src_h, out_h, frame_h
+
+    # with the scatter / gather-v legs: rank 0's GPU holds the whole buffer and receives all frames
+    sg = None
+    if world > 1:
+        full = one_h.to(dev).repeat(nchunks) if rank == 0 else None
+        kw = dict(clevel=clevel, doshuffle=shuf, typesize=head_ts, compressor=comp_name)
+        for rep in range(2):                                   # rep 0 warms NCCL's P2P channels
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier(); e0.record()
+            frames, sizes = sharding.compress_sharded(pkg, dist, full, total, chunk, rank, world, dev, **kw)
+            back = sharding.decompress_sharded(pkg, dist, frames, sizes, total, chunk, rank, world, dev)
+            e1.record(); torch.cuda.synchronize()
+            (ms_sg,) = reduce_max([e0.elapsed_time(e1)])
+            barrier()
+        if rank == 0:
+            assert torch.equal(back, full)
+            sg = {"value": 2 * total / (ms_sg / 1e3) / 1e9, "unit": "GB/s", "ms": ms_sg,
+                  "note": "rank 0 scatters 8 GiB over NCCL/NVLink, gathers the frames, scatters them back and gathers the decoded slices"}
+        del full, back, frames
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, hbm_src = peaks()
+    ms, tc, td, fb = head
+    per_step = ms / args.steps / 1e3
+    cb_chunk = (fb - 32 - 8 * k) // k
+    enc_ms, enc_n = prof["encode"]
+    enc_avg = enc_ms / max(enc_n, 1) / 1e3
+    achieved = (chunk + cb_chunk) / enc_avg / 1e9 if enc_avg > 0 else 0.0
+    agg = 2 * (total + nchunks * cb_chunk) / per_step / 1e9
+    line = {"metric": METRIC, "value": 2 * total / per_step / 1e9, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "compress_gbs": total / (tc / args.steps) / 1e9, "decompress_gbs": total / (td / args.steps) / 1e9,
+            "ratio": chunk / cb_chunk, "cbytes": nchunks * cb_chunk, "typesize_sweep": sweep_out,
+            "e2e": {"value": 2 * total / (ms_h / args.steps / 1e3) / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": mine + fb, "d2h_bytes_per_step": fb + mine,
+                    "compress_gbs": total / (tc_h / args.steps) / 1e9, "decompress_gbs": total / (td_h / args.steps) / 1e9},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "encode_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_launch": chunk + cb_chunk, "avg_launch_ms": enc_avg * 1e3,
+                         "note": "per launch, while up to 4 chunks per GPU are in flight",
+                         "whole_step": {"achieved": agg / world, "frac": agg / world / hbm,
+                                        "note": "algorithmic bytes of the whole step (both directions) / step time, per GPU"}},
+            "kernels": {kk: {"ms_avg": (v[0] / v[1] if v[1] else 0.0), "launches": v[1]} for kk, v in prof.items()}}
+    if sg:
+        line["with_scatter_gather"] = sg
+    if world == 1:
+        cpu = cpu_chunks(np, comp_name, shuf, head_ts, clevel, chunk, 4, host_threads)
+        t = cpu["tc"] + cpu["td"]
+        line["cpu_baseline"] = {"value": 2 * cpu["bytes"] / t / 1e9, "unit": "GB/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                "sample": f"4 of the {nchunks} chunks, one after another, blosc_*_ctx with nthreads={cpu['cores']}",
+                                "compress_gbs": cpu["bytes"] / cpu["tc"] / 1e9, "decompress_gbs": cpu["bytes"] / cpu["td"] / 1e9}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(SHARDED))
     ap.add_argument("--cpu-threads", type=int, default=0)
     args = ap.parse_args()
     import numpy as np
@@ -176,6 +383,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in SHARDED:
+        return run_sharded(args, np, rank, world, local_rank)
     comp_name, shuf, ts, clevel, nbytes = WORKLOADS[args.workload]
     host_threads = args.cpu_threads or min(len(os.sched_getaffinity(0)) or 1, 256)
     config = {"workload": args.workload, "codec": comp_name, "filter": ["none", "shuffle", "bitshuffle"][shuf], "typesize": ts,

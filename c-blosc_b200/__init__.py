@@ -52,6 +52,19 @@ def _load(path: str) -> C.CDLL:
     lib.blosc_set_splitmode.argtypes = [ci]
     lib.blosc_set_blocksize.argtypes = [sz]
     lib.blosc_cbuffer_sizes.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    ll = C.c_longlong
+    lib.blosc_b200_frame_bound.restype = sz
+    lib.blosc_b200_frame_bound.argtypes = [sz, sz, sz]
+    lib.blosc_b200_frame_compress.restype = ll
+    lib.blosc_b200_frame_compress.argtypes = [ci, ci, sz, sz, vp, vp, sz, C.c_char_p, sz, sz, ci]
+    lib.blosc_b200_frame_decompress.restype = ll
+    lib.blosc_b200_frame_decompress.argtypes = [vp, sz, vp, sz, ci]
+    lib.blosc_b200_frame_getitem.restype = ll
+    lib.blosc_b200_frame_getitem.argtypes = [vp, sz, sz, sz, vp]
+    lib.blosc_b200_frame_info.restype = ci
+    lib.blosc_b200_frame_info.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    lib.blosc_b200_frame_chunk.restype = ll
+    lib.blosc_b200_frame_chunk.argtypes = [vp, sz, sz, C.POINTER(sz)]
     return lib
 
 
@@ -90,6 +103,45 @@ def decompress_ctx(src, dest, destsize, numinternalthreads=1):
 def getitem(src, start, nitems, dest):
     """blosc_getitem (reference blosc.h:312)."""
     return lib.blosc_getitem(_ptr(src), start, nitems, _ptr(dest))
+
+
+def _name(compressor):
+    return compressor.encode() if isinstance(compressor, str) else compressor
+
+
+def frame_bound(nbytes, typesize=1, chunksize=0) -> int:
+    """Worst-case size of a frame (blosc_b200_frame_bound)."""
+    return int(lib.blosc_b200_frame_bound(nbytes, typesize, chunksize))
+
+
+def frame_compress(clevel, doshuffle, typesize, nbytes, src, dest, destsize, compressor, blocksize=0, chunksize=0,
+                   numinternalthreads=1):
+    """Buffers of any size as a sequence of independent Blosc-1 chunks, several in flight."""
+    return int(lib.blosc_b200_frame_compress(clevel, doshuffle, typesize, nbytes, _ptr(src), _ptr(dest), destsize,
+                                             _name(compressor), blocksize, chunksize, numinternalthreads))
+
+
+def frame_decompress(frame, framesize, dest, destsize, numinternalthreads=1):
+    return int(lib.blosc_b200_frame_decompress(_ptr(frame), framesize, _ptr(dest), destsize, numinternalthreads))
+
+
+def frame_getitem(frame, framesize, start, nitems, dest):
+    return int(lib.blosc_b200_frame_getitem(_ptr(frame), framesize, start, nitems, _ptr(dest)))
+
+
+def frame_info(frame, framesize):
+    """(nbytes, cbytes, chunksize, nchunks) or None if `frame` is not a valid frame."""
+    v = [C.c_size_t(0) for _ in range(4)]
+    if lib.blosc_b200_frame_info(_ptr(frame), framesize, *[C.byref(x) for x in v]) != 0:
+        return None
+    return tuple(int(x.value) for x in v)
+
+
+def frame_chunk(frame, framesize, i):
+    """(offset, cbytes) of chunk i inside the frame, or None."""
+    n = C.c_size_t(0)
+    off = lib.blosc_b200_frame_chunk(_ptr(frame), framesize, i, C.byref(n))
+    return None if off < 0 else (int(off), int(n.value))
 
 
 def filter_block(mode, typesize, blocksize, src, dest):

@@ -425,6 +425,16 @@ static void make_header(uint8_t* h, int versionlz, int flags, int typesize, int3
   wr_i32(h + 4, nbytes); wr_i32(h + 8, blocksize); wr_i32(h + 12, cbytes);
 }
 
+/* Where a finished chunk goes.  The plain API writes at `dest`; a frame (below) learns the
+ * chunk's offset only once every earlier chunk has announced its size, so the compressor asks
+ * for the final location at the moment `cbytes` is known. */
+typedef struct b2_frame_job b2_frame_job;
+typedef struct {
+  b2_frame_job* job;
+  int index, placed;
+} b2_place;
+static void* frame_place(b2_place* pl, int32_t cbytes);
+
 /* header + raw payload (blosc.c:825-830) */
 static int emit_memcpyed(const uint8_t* hdr, const void* src, int src_dev, void* dest, int dest_dev, int32_t nbytes) {
   b2_ws* w = NULL;
@@ -439,8 +449,9 @@ static int emit_memcpyed(const uint8_t* hdr, const void* src, int src_dev, void*
 /* ------------------------------------------------------------------------- */
 /* compression                                                                */
 /* ------------------------------------------------------------------------- */
-int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src, void* dest,
-                       size_t destsize, const char* compressor, size_t blocksize, int numinternalthreads) {
+static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src, void* dest,
+                         size_t destsize, const char* compressor, size_t blocksize, int numinternalthreads,
+                         b2_place* pl, int pl_dest_dev) {
   const int compcode = blosc_compname_to_compcode(compressor);
   int32_t ts, nb, bs, nblocks, leftover, dsz;
   int flags = 0, compformat, dont_split, src_dev, dest_dev, dofilter, fmode = 0, nsplits, result = -1;
@@ -480,13 +491,14 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
   flags |= compformat << 5;
 
   src_dev = (nb > 0) ? b2_ptr_is_device(src) : 0;
-  dest_dev = b2_ptr_is_device(dest);
+  dest_dev = pl ? pl_dest_dev : b2_ptr_is_device(dest);
 
   /* blosc_compress_context, blosc.c:1250-1279 */
   if ((flags & BLOSC_MEMCPYED) && nb + BLOSC_MAX_OVERHEAD > dsz) return 0;
   if (check_threads(numinternalthreads, nb, bs) < 0) return -1;
   if (flags & BLOSC_MEMCPYED) {
     make_header(hdr, 1, flags, ts, nb, bs, nb + 16);
+    if (pl && !(dest = frame_place(pl, nb + 16))) return 0;
     return emit_memcpyed(hdr, src, src_dev, dest, dest_dev, nb);
   }
 
@@ -540,7 +552,7 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     sa.bstarts = (int*)w->bstarts.p; sa.result = w->d_result;
     sa.nsplits = nsplits; sa.nfull = nfull; sa.has_leftover = leftover > 0; sa.destsize = dsz;
     if (b2_launch_scan(&sa, w->stream)) break;
-    if (dest_dev) d_dest = (uint8_t*)dest;
+    if (dest_dev && !pl) d_dest = (uint8_t*)dest;
     else { if (buf_ensure(&w->out, (size_t)dsz + 64)) break; d_dest = (uint8_t*)w->out.p; }
     ca.map = ea.map; ca.in = d_codec_in; ca.slots = ea.slots; ca.csizes = ea.csizes; ca.bstarts = sa.bstarts;
     ca.result = w->d_result; ca.dest = d_dest;
@@ -551,15 +563,18 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
     if (b2_stream_sync(w->stream)) break;
     if (w->h_result[1]) {                                                 /* fits */
       const int32_t cbytes = w->h_result[0];
+      if (pl && !(dest = frame_place(pl, cbytes))) { result = 0; break; }
       if (!dest_dev) {
         if (d2h_any(w, dest, d_dest, (size_t)cbytes)) break;
+      } else if (pl) {
+        if (copy_any(dest, 1, d_dest, 1, (size_t)cbytes, w->stream)) break;
       }
       result = cbytes;
     } else if (nb + BLOSC_MAX_OVERHEAD <= dsz) {                          /* blosc.c:1264-1272 */
       result = -2;   /* marker: redo as MEMCPYED after releasing the workspace */
     } else {
       make_header(hdr, 1, flags, ts, nb, bs, 0);                          /* blosc.c:1275 with ntbytes == 0 */
-      if (copy_any(dest, dest_dev, hdr, 0, 16, w->stream)) break;
+      if (!pl && copy_any(dest, dest_dev, hdr, 0, 16, w->stream)) break;
       result = 0;
     }
   } while (0);
@@ -567,9 +582,16 @@ int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes
   if (result == -2) {
     flags |= BLOSC_MEMCPYED;
     make_header(hdr, 1, flags, ts, nb, bs, nb + 16);
+    if (pl && !(dest = frame_place(pl, nb + 16))) return 0;
     return emit_memcpyed(hdr, src, src_dev, dest, dest_dev, nb);
   }
   return result;
+}
+
+int blosc_compress_ctx(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src, void* dest,
+                       size_t destsize, const char* compressor, size_t blocksize, int numinternalthreads) {
+  return compress_impl(clevel, doshuffle, typesize, nbytes, src, dest, destsize, compressor, blocksize,
+                       numinternalthreads, NULL, 0);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -760,6 +782,323 @@ int blosc_getitem(const void* src, int start, int nitems, void* dest) {    /* bl
     result = (int)(b_hi - b_lo);
   } while (0);
   ws_release(w);
+  return result;
+}
+
+/* ------------------------------------------------------------------------- */
+/* frames: buffers larger than one chunk           */
+/* ------------------------------------------------------------------------- */
+/* A Blosc-1 chunk holds at most INT_MAX-16 bytes (blosc.h:40) and a single call keeps the GPU
+ * about 7 % busy, so large buffers are cut into independent chunks that
+ * are compressed by a few host threads at once, each on its own workspace and stream: chunk
+ * i+1's PCIe transfer and filter overlap chunk i's codec kernels.  The container is a minimal
+ * index in front of ordinary chunks, every one of which the reference library can decode:
+ *
+ *   0   "B2FR"            magic
+ *   4   u8 version (1), 3 reserved bytes (0)
+ *   8   u64 nbytes        uncompressed size of the whole frame
+ *   16  u64 cbytes        size of the frame itself
+ *   24  u32 chunksize     uncompressed bytes per chunk (the last one may be shorter)
+ *   28  u32 nchunks
+ *   32  u64 offset[nchunks]   from the start of the frame
+ *   ..  the chunks, back to back, in order
+ */
+#define B2_FRAME_HDR 32
+#define B2_FRAME_DEFAULT_CHUNK ((size_t)256 << 20)
+#define B2_FRAME_MAX_WORKERS 8
+
+struct b2_frame_job {
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int next, commit, failed, err, nchunks, dev, dest_dev, workers;
+  /* compression */
+  int clevel, doshuffle, nthreads;
+  size_t typesize, blocksize, chunksize, nbytes, destsize, cursor;
+  const char* compressor;
+  const uint8_t* src;
+  uint8_t* dest;
+  uint64_t* offsets;
+  /* decompression */
+  const uint8_t* frame;
+};
+
+static void wr_u64(uint8_t* p, uint64_t v) { int i; for (i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i)); }
+static uint64_t rd_u64(const uint8_t* p) { uint64_t v = 0; int i; for (i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
+static void wr_u32(uint8_t* p, uint32_t v) { wr_i32(p, (int32_t)v); }
+static uint32_t rd_u32(const uint8_t* p) { return (uint32_t)rd_i32(p); }
+
+static int frame_workers(int nchunks) {
+  const char* e = getenv("BLOSC_B200_FRAME_WORKERS");
+  int n = e ? atoi(e) : 4;
+  if (n < 1) n = 1;
+  if (n > B2_FRAME_MAX_WORKERS) n = B2_FRAME_MAX_WORKERS;
+  return n < nchunks ? n : nchunks;
+}
+
+/* Ordered commit: chunk `index` gets the bytes right after chunk index-1.  Returns NULL (and
+ * marks the job failed) when the frame does not fit; cbytes < 0 gives up the turn after an error. */
+static void* frame_place(b2_place* pl, int32_t cbytes) {
+  b2_frame_job* j = pl->job;
+  void* where = NULL;
+  pthread_mutex_lock(&j->mu);
+  while (j->commit != pl->index) pthread_cond_wait(&j->cv, &j->mu);
+  if (cbytes >= 0 && !j->failed && j->cursor + (size_t)cbytes <= j->destsize) {
+    j->offsets[pl->index] = j->cursor;
+    where = j->dest + j->cursor;
+    j->cursor += (size_t)cbytes;
+  } else j->failed = 1;
+  pl->placed = 1;
+  j->commit++;
+  pthread_cond_broadcast(&j->cv);
+  pthread_mutex_unlock(&j->mu);
+  return where;
+}
+
+static int frame_take(b2_frame_job* j, int* failed) {
+  int i;
+  pthread_mutex_lock(&j->mu);
+  i = j->next < j->nchunks ? j->next++ : -1;
+  *failed = j->failed;
+  pthread_mutex_unlock(&j->mu);
+  return i;
+}
+
+static void frame_fail(b2_frame_job* j, int rc) {
+  pthread_mutex_lock(&j->mu);
+  j->failed = 1;
+  if (rc < 0 && !j->err) j->err = rc;
+  pthread_mutex_unlock(&j->mu);
+}
+
+static void* frame_compress_worker(void* arg) {
+  b2_frame_job* j = (b2_frame_job*)arg;
+  int i, failed;
+  b2_set_device(j->dev);
+  while ((i = frame_take(j, &failed)) >= 0) {
+    b2_place pl;
+    const size_t off = (size_t)i * j->chunksize;
+    const size_t n = j->nbytes - off < j->chunksize ? j->nbytes - off : j->chunksize;
+    int rc = -1;
+    pl.job = j; pl.index = i; pl.placed = 0;
+    if (!failed)
+      rc = compress_impl(j->clevel, j->doshuffle, j->typesize, n, j->src + off, NULL, n + BLOSC_MAX_OVERHEAD,
+                         j->compressor, j->blocksize, j->nthreads, &pl, j->dest_dev);
+    if (!pl.placed) frame_place(&pl, -1);
+    if (rc <= 0 && !failed) frame_fail(j, rc);
+  }
+  return NULL;
+}
+
+static void* frame_decompress_worker(void* arg) {
+  b2_frame_job* j = (b2_frame_job*)arg;
+  int i, failed;
+  b2_set_device(j->dev);
+  while ((i = frame_take(j, &failed)) >= 0) {
+    const size_t off = (size_t)i * j->chunksize;
+    const size_t n = j->nbytes - off < j->chunksize ? j->nbytes - off : j->chunksize;
+    int rc;
+    if (failed) continue;
+    rc = blosc_decompress_ctx(j->frame + j->offsets[i], j->dest + off, n, j->nthreads);
+    if (rc != (int)n) frame_fail(j, -1);
+  }
+  return NULL;
+}
+
+static int frame_run(b2_frame_job* j, void* (*fn)(void*)) {
+  pthread_t th[B2_FRAME_MAX_WORKERS];
+  int k, started = 0;
+  pthread_mutex_init(&j->mu, NULL);
+  pthread_cond_init(&j->cv, NULL);
+  j->dev = b2_get_device();
+  for (k = 1; k < j->workers; k++) {
+    if (pthread_create(&th[started], NULL, fn, j) != 0) break;
+    started++;
+  }
+  fn(j);                                   /* the calling thread is worker 0 */
+  for (k = 0; k < started; k++) pthread_join(th[k], NULL);
+  pthread_cond_destroy(&j->cv);
+  pthread_mutex_destroy(&j->mu);
+  return j->failed ? -1 : 0;
+}
+
+static size_t frame_chunksize(size_t chunksize, size_t typesize) {
+  if (chunksize == 0) chunksize = B2_FRAME_DEFAULT_CHUNK;
+  if (chunksize > BLOSC_MAX_BUFFERSIZE) chunksize = BLOSC_MAX_BUFFERSIZE;
+  if (typesize > 1 && typesize <= BLOSC_MAX_TYPESIZE && chunksize >= typesize) chunksize -= chunksize % typesize;
+  return chunksize;
+}
+
+size_t blosc_b200_frame_bound(size_t nbytes, size_t typesize, size_t chunksize) {
+  size_t nchunks;
+  chunksize = frame_chunksize(chunksize, typesize);
+  nchunks = (nbytes + chunksize - 1) / chunksize;
+  return B2_FRAME_HDR + nchunks * (8 + BLOSC_MAX_OVERHEAD) + nbytes;
+}
+
+long long blosc_b200_frame_compress(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src,
+                                    void* dest, size_t destsize, const char* compressor, size_t blocksize,
+                                    size_t chunksize, int numinternalthreads) {
+  b2_frame_job j;
+  uint8_t* index;
+  size_t nchunks, index_bytes;
+  int i, rc, dest_dev;
+
+  if (clevel < 0 || clevel > 9) return -10;                       /* same codes as the chunk API */
+  if (doshuffle != 0 && doshuffle != 1 && doshuffle != 2) return -10;
+  if (typesize == 0) return -10;
+  if (blosc_compname_to_compcode(compressor) != BLOSC_BLOSCLZ && blosc_compname_to_compcode(compressor) != BLOSC_LZ4) return -5;
+  chunksize = frame_chunksize(chunksize, typesize);
+  nchunks = (nbytes + chunksize - 1) / chunksize;
+  if (nchunks > 0x7fffffff / 2) return -1;
+  index_bytes = B2_FRAME_HDR + nchunks * 8;
+  if (destsize < index_bytes) return 0;
+  if (!backend_ready()) return -1;
+  dest_dev = b2_ptr_is_device(dest);
+
+  memset(&j, 0, sizeof j);
+  j.nchunks = (int)nchunks; j.workers = frame_workers((int)nchunks); j.dest_dev = dest_dev;
+  j.clevel = clevel; j.doshuffle = doshuffle; j.nthreads = numinternalthreads;
+  j.typesize = typesize; j.blocksize = blocksize; j.chunksize = chunksize; j.nbytes = nbytes;
+  j.destsize = destsize; j.cursor = index_bytes; j.compressor = compressor;
+  j.src = (const uint8_t*)src; j.dest = (uint8_t*)dest;
+  j.offsets = (uint64_t*)calloc(nchunks ? nchunks : 1, sizeof(uint64_t));
+  index = (uint8_t*)malloc(index_bytes);
+  if (!j.offsets || !index) { free(j.offsets); free(index); return -1; }
+  rc = nchunks ? frame_run(&j, frame_compress_worker) : 0;
+  if (rc == 0) {
+    memcpy(index, "B2FR", 4); index[4] = 1; index[5] = index[6] = index[7] = 0;
+    wr_u64(index + 8, (uint64_t)nbytes); wr_u64(index + 16, (uint64_t)j.cursor);
+    wr_u32(index + 24, (uint32_t)chunksize); wr_u32(index + 28, (uint32_t)nchunks);
+    for (i = 0; i < (int)nchunks; i++) wr_u64(index + B2_FRAME_HDR + 8 * (size_t)i, j.offsets[i]);
+    if (dest_dev) {
+      b2_ws* w = ws_acquire();
+      rc = w ? copy_any(dest, 1, index, 0, index_bytes, w->stream) : -1;
+      if (w) ws_release(w);
+    } else memcpy(dest, index, index_bytes);
+  }
+  free(j.offsets); free(index);
+  if (rc) return j.err ? j.err : (j.failed ? 0 : -1);            /* 0: does not fit in destsize, as blosc_compress */
+  return (long long)j.cursor;
+}
+
+/* reads and validates the index; *offsets is malloc'ed (nchunks+1 entries, the last one = cbytes) */
+static int frame_open(const void* frame, size_t framesize, size_t* nbytes, size_t* chunksize, size_t* nchunks,
+                      uint64_t** offsets) {
+  uint8_t hb[B2_FRAME_HDR];
+  uint8_t* raw;
+  uint64_t* off;
+  uint64_t cbytes;
+  size_t n, k;
+  const int dev = b2_ptr_is_device(frame);
+  b2_ws* w = NULL;
+  int rc = 0;
+  if (framesize < B2_FRAME_HDR) return -1;
+  if (dev) {
+    w = ws_acquire();
+    if (!w) return -1;
+    rc = copy_any(hb, 0, frame, 1, B2_FRAME_HDR, w->stream);
+    if (rc) { ws_release(w); return -1; }
+  } else memcpy(hb, frame, B2_FRAME_HDR);
+  rc = -1;
+  do {
+    if (memcmp(hb, "B2FR", 4) != 0 || hb[4] != 1) break;
+    *nbytes = (size_t)rd_u64(hb + 8); cbytes = rd_u64(hb + 16);
+    *chunksize = rd_u32(hb + 24); n = rd_u32(hb + 28);
+    if (cbytes > framesize || cbytes < B2_FRAME_HDR + 8 * (uint64_t)n) break;
+    if (*nbytes > 0 && (*chunksize == 0 || *chunksize > BLOSC_MAX_BUFFERSIZE)) break;
+    if (n != (*nbytes ? (*nbytes + *chunksize - 1) / *chunksize : 0)) break;
+    raw = (uint8_t*)malloc(8 * n + 8);
+    off = (uint64_t*)malloc(8 * (n + 1));
+    if (!raw || !off) { free(raw); free(off); break; }
+    if (dev) { if (copy_any(raw, 0, (const uint8_t*)frame + B2_FRAME_HDR, 1, 8 * n, w->stream)) { free(raw); free(off); break; } }
+    else memcpy(raw, (const uint8_t*)frame + B2_FRAME_HDR, 8 * n);
+    for (k = 0; k < n; k++) off[k] = rd_u64(raw + 8 * k);
+    off[n] = cbytes;
+    free(raw);
+    rc = 0;
+    for (k = 0; k < n; k++)                /* chunks in order, at least a header each, inside the frame */
+      if (off[k] < B2_FRAME_HDR + 8 * (uint64_t)n || off[k + 1] < off[k] + BLOSC_MAX_OVERHEAD || off[k + 1] > cbytes) rc = -1;
+    if (rc) { free(off); break; }
+    *nchunks = n; *offsets = off;
+  } while (0);
+  if (w) ws_release(w);
+  return rc;
+}
+
+int blosc_b200_frame_info(const void* frame, size_t framesize, size_t* nbytes, size_t* cbytes, size_t* chunksize,
+                          size_t* nchunks) {
+  size_t nb = 0, cs = 0, nc = 0;
+  uint64_t* off = NULL;
+  if (!backend_ready()) return -1;
+  if (frame_open(frame, framesize, &nb, &cs, &nc, &off)) return -1;
+  if (nbytes) *nbytes = nb;
+  if (cbytes) *cbytes = (size_t)off[nc];
+  if (chunksize) *chunksize = cs;
+  if (nchunks) *nchunks = nc;
+  free(off);
+  return 0;
+}
+
+long long blosc_b200_frame_chunk(const void* frame, size_t framesize, size_t i, size_t* chunk_cbytes) {
+  size_t nb = 0, cs = 0, nc = 0;
+  uint64_t* off = NULL;
+  long long r;
+  if (!backend_ready()) return -1;
+  if (frame_open(frame, framesize, &nb, &cs, &nc, &off)) return -1;
+  if (i >= nc) { free(off); return -1; }
+  if (chunk_cbytes) *chunk_cbytes = (size_t)(off[i + 1] - off[i]);
+  r = (long long)off[i];
+  free(off);
+  return r;
+}
+
+long long blosc_b200_frame_decompress(const void* frame, size_t framesize, void* dest, size_t destsize,
+                                      int numinternalthreads) {
+  b2_frame_job j;
+  size_t nb = 0, cs = 0, nc = 0;
+  uint64_t* off = NULL;
+  int rc;
+  if (!backend_ready()) return -1;
+  if (frame_open(frame, framesize, &nb, &cs, &nc, &off)) return -1;
+  if (nb > destsize) { free(off); return -1; }
+  memset(&j, 0, sizeof j);
+  j.nchunks = (int)nc; j.workers = frame_workers((int)nc); j.nthreads = numinternalthreads;
+  j.chunksize = cs; j.nbytes = nb; j.frame = (const uint8_t*)frame; j.dest = (uint8_t*)dest; j.offsets = off;
+  rc = nc ? frame_run(&j, frame_decompress_worker) : 0;
+  free(off);
+  return rc ? -1 : (long long)nb;
+}
+
+long long blosc_b200_frame_getitem(const void* frame, size_t framesize, size_t start, size_t nitems, void* dest) {
+  size_t nb = 0, cs = 0, nc = 0, ts = 0, ipc, done = 0;
+  uint64_t* off = NULL;
+  uint8_t hb[16];
+  long long result = -1;
+  if (!backend_ready()) return -1;
+  if (frame_open(frame, framesize, &nb, &cs, &nc, &off)) return -1;
+  do {
+    if (nc == 0) { result = nitems == 0 ? 0 : -1; break; }
+    if (b2_ptr_is_device(frame)) {
+      b2_ws* w = ws_acquire();
+      int rc = w ? copy_any(hb, 0, (const uint8_t*)frame + off[0], 1, 16, w->stream) : -1;
+      if (w) ws_release(w);
+      if (rc) break;
+    } else memcpy(hb, (const uint8_t*)frame + off[0], 16);
+    ts = hb[3];
+    if (ts == 0 || cs % ts) break;
+    ipc = cs / ts;                                     /* items per chunk */
+    if (start > nb / ts || nitems > nb / ts - start) { fprintf(stderr, "`start`+`nitems` out of bounds"); break; }
+    result = 0;
+    while (done < nitems) {
+      const size_t c = (start + done) / ipc, first = (start + done) % ipc;
+      const size_t take = nitems - done < ipc - first ? nitems - done : ipc - first;
+      const int rc = blosc_getitem((const uint8_t*)frame + off[c], (int)first, (int)take, (uint8_t*)dest + done * ts);
+      if (rc != (int)(take * ts)) { result = rc < 0 ? rc : -1; break; }
+      done += take;
+      result += rc;
+    }
+  } while (0);
+  free(off);
   return result;
 }
 

@@ -126,6 +126,26 @@ const char* blosc_cbuffer_complib(const void* cbuffer);                         
  * src/dest host or device.  Returns 0, or -1 on device failure. */
 int blosc_b200_filter(int mode, size_t typesize, size_t blocksize, const void* src, void* dest);
 
+/* Frames: buffers larger than one chunk (a Blosc-1 chunk holds at most BLOSC_MAX_BUFFERSIZE
+ * bytes, blosc.h:40).  The buffer is cut into `chunksize`-byte pieces (0 = 256 MiB; rounded down
+ * to a multiple of typesize), each compressed exactly as blosc_compress_ctx() would with
+ * destsize = piece + 16, several in flight at once so that PCIe transfers overlap the kernels.
+ * The result is a 32-byte header + u64 offset table + ordinary Blosc-1 chunks (layout in
+ * blosc_b200.c); blosc_b200_frame_chunk() locates chunk i so that any Blosc-1 library can decode
+ * it.  src/dest/frame may be host or device memory.  Returns: compress -> frame bytes, 0 if it
+ * does not fit in destsize (always fits in blosc_b200_frame_bound()), <0 like blosc_compress_ctx;
+ * decompress -> nbytes or -1; getitem -> bytes copied or <0 (items may span chunks). */
+size_t    blosc_b200_frame_bound(size_t nbytes, size_t typesize, size_t chunksize);
+long long blosc_b200_frame_compress(int clevel, int doshuffle, size_t typesize, size_t nbytes, const void* src,
+                                    void* dest, size_t destsize, const char* compressor, size_t blocksize,
+                                    size_t chunksize, int numinternalthreads);
+long long blosc_b200_frame_decompress(const void* frame, size_t framesize, void* dest, size_t destsize,
+                                      int numinternalthreads);
+long long blosc_b200_frame_getitem(const void* frame, size_t framesize, size_t start, size_t nitems, void* dest);
+int       blosc_b200_frame_info(const void* frame, size_t framesize, size_t* nbytes, size_t* cbytes,
+                                size_t* chunksize, size_t* nchunks);
+long long blosc_b200_frame_chunk(const void* frame, size_t framesize, size_t i, size_t* chunk_cbytes);
+
 /* Select the CUDA device used by the calling thread's subsequent calls with HOST pointers
  * (device pointers carry their device).  Multi-GPU callers run one process (or thread) per GPU. */
 int blosc_b200_set_device(int dev);

@@ -1,6 +1,7 @@
 /* simt_emu.cpp -- TEST INFRASTRUCTURE ONLY (see simt_emu.h). */
 #include "simt_emu.h"
 
+#include <mutex>
 #include <vector>
 
 namespace simt {
@@ -107,7 +108,10 @@ static void resolve_warp(Thread* th, unsigned base, unsigned nlanes, bool* did) 
   }
 }
 
+static std::mutex g_launch_mu;   /* the scheduler state is global: one emulated kernel at a time */
+
 void launch(Dim3 grid, Dim3 block, size_t dynsmem, const std::function<void()>& body) {
+  std::lock_guard<std::mutex> guard(g_launch_mu);
   unsigned nthreads = block.x * block.y * block.z;
   std::vector<Thread> th(nthreads);
   std::vector<unsigned char> smem(dynsmem + 64);

@@ -1,58 +1,85 @@
-"""Multi-GPU logic on CPU: world_size-2 gloo run of the chunk sharding used by bench.py --gpus N
-(independent chunks per rank, no data-path collective; only sizes and times are reduced)."""
+"""Multi-GPU logic on CPU: a world_size-2 gloo run of the PRODUCT's sharding code
+(c-blosc_b200/sharding.py: scatter slices -> per-rank frame compress -> gather-v, and the mirror)
+with the library's host code running over the emulated backend.  The root checks that every chunk
+of every rank's frame is byte-identical to the oracle's chunk for that slice of the buffer."""
+import ctypes as C
 import os
 import socket
+import sys
 
 import numpy as np
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from datagen import bench_words
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "_build", "libblosc_b200_emu.so")
+TOTAL, CHUNK, TS = 5 * 40000 + 1234, 40000, 4          # 6 chunks: ranks get 3 + 3, the last one short
 
 
-def shard_plan(total_chunks, world):
-    """chunk c belongs to rank c // ceil(total/world): contiguous slices, as SURVEY section 8e."""
-    per = (total_chunks + world - 1) // world
-    return [list(range(r * per, min((r + 1) * per, total_chunks))) for r in range(world)]
+def _data():
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from datagen import bench_words, gen
+    return np.concatenate([bench_words(120000), gen("text", 50000, 5), gen("rand", TOTAL - 170000, 6)])
 
 
-def _worker(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      BLOSC_B200_LIB=EMU, BLOSC_B200_FRAME_WORKERS="2")
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    from cblosc_b200 import sharding
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    plan = shard_plan(5, world)
-    mine = plan[rank]
-    # each rank "compresses" its own chunks: here a deterministic stand-in size per chunk
-    sizes = torch.tensor([int(bench_words(4096, start=c * 1024).sum()) % 100000 for c in mine] + [0] * (3 - len(mine)), dtype=torch.int64)
-    gathered = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(gathered, sizes)
+    full = torch.from_numpy(_data()) if rank == 0 else None
+    frames, sizes = sharding.compress_sharded(pkg, dist, full, TOTAL, CHUNK, rank, world, "cpu", clevel=5, doshuffle=1,
+                                              typesize=TS, compressor="lz4")
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # bench.py's max-over-ranks reduction
+    back = sharding.decompress_sharded(pkg, dist, frames, sizes, TOTAL, CHUNK, rank, world, "cpu")
     if rank == 0:
-        out.put(([g.tolist() for g in gathered], t.item(), plan))
+        q.put(([f.numpy().copy() for f in frames], sizes, back.numpy().copy(), t.item()))
+    dist.barrier()
     dist.destroy_process_group()
 
 
-def test_shard_plan_covers_everything():
+def test_shard_plan_covers_everything(pkg):
+    from cblosc_b200 import sharding
     for total in (1, 4, 5, 32):
         for world in (1, 2, 4, 8):
-            plan = shard_plan(total, world)
-            flat = [c for p in plan for c in p]
-            assert flat == list(range(total))
+            plan = sharding.shard_plan(total, world)
+            assert [c for p in plan for c in p] == list(range(total))
+    assert sharding.shard_plan(32, 8)[3] == [12, 13, 14, 15]        # GPU g gets chunks 4g..4g+3
+    rg = sharding.byte_ranges(TOTAL, CHUNK, 2)
+    assert rg == [(0, 3 * CHUNK), (3 * CHUNK, TOTAL)]
+    assert sharding.byte_ranges(10, 4, 8)[3:] == [(10, 10)] * 5     # more ranks than chunks: empty tails
 
 
-def test_two_rank_gloo():
+def test_two_rank_gloo_sharded_roundtrip(emu, orc):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    gathered, tmax, plan = q.get(timeout=120)
+    frames, sizes, back, tmax = q.get(timeout=300)
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
-    assert tmax == 2.0                                  # max over ranks
-    assert plan == [[0, 1, 2], [3, 4]]
-    want = [int(bench_words(4096, start=c * 1024).sum()) % 100000 for c in range(5)]
-    assert gathered[0] == want[:3] and gathered[1][:2] == want[3:]
+    src = _data()
+    assert tmax == 2.0
+    assert (back == src).all()
+    # every chunk of every rank's frame == the oracle's chunk of that slice (chunks are reference chunks)
+    from datagen import compress
+    bounds = [(0, 3 * CHUNK), (3 * CHUNK, TOTAL)]
+    for r, (lo, hi) in enumerate(bounds):
+        f = frames[r]
+        assert len(f) == sizes[r] and bytes(f[:4]) == b"B2FR"
+        nchunks = int(np.frombuffer(f[28:32].tobytes(), "<u4")[0])
+        assert nchunks == 3
+        offs = np.frombuffer(f[32:32 + 8 * nchunks].tobytes(), "<u8")
+        for i in range(nchunks):
+            piece = src[lo + i * CHUNK:min(lo + (i + 1) * CHUNK, hi)]
+            rc, want = compress(orc, "orc_compress_ctx", 5, 1, TS, piece, len(piece) + 16, "lz4")
+            o = int(offs[i])
+            assert (f[o:o + rc] == want[:rc]).all()

@@ -85,6 +85,26 @@ DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
 #endif
 }
 
+/* L1 prefetch of the line holding byte p of a stream of `end` bytes (no-op past the end) */
+DEV void lz4d_prefetch(const u8* base, int p, int end) {
+#ifndef SIMT_EMU
+  if (p < end) asm volatile("prefetch.global.L1 [%0];" :: "l"(base + p));
+#else
+  (void)base; (void)p; (void)end;
+#endif
+}
+
+/* 4 bytes at position p; touches at most byte p+7 */
+DEV u32 ldp_win4(const StreamBase& sb, int p) {
+#ifdef SIMT_EMU
+  u32 b0; memcpy(&b0, sb.s + p, 4); return b0;
+#else
+  const int q = p + sb.sal;
+  const u32* w = sb.s32 + (q >> 2);
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), (u32)(q & 3) * 8u);
+#endif
+}
+
 template <bool U16>
 DEV u32 lz4_hash_seq(u32 lo, u32 b4) {                        /* lz4.c:777-806 on bytes already in registers */
   if (U16) return (lo * 2654435761u) >> (32 - 13);
@@ -399,7 +419,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
 
 /* ---- decoder ---- */
 #ifdef SIMT_EMU
-static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d_general_seqs = 0;
+static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d_general_seqs = 0, g_dbg_lz4d_dense_seqs = 0;
 #define LZ4D_DBG(x) do { if (lane == 0) (x)++; } while (0)
 #define LZ4D_DBGN(x, n) do { if (lane == 0) (x) += (n); } while (0)
 #else
@@ -409,6 +429,8 @@ static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d
 #define LZ4D_RING 16384                      /* bytes of recent output mirrored in shared memory, per warp */
 #define LZ4D_RMASK (LZ4D_RING - 1)
 #define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 26) */
+#define LZ4D_DENSE_OUT 640                   /* a dense batch writes <= 32 x 18 bytes */
+#define LZ4D_DENSE_MIN 4                     /* fewer chained 3-byte sequences than this: the 11-wide batch path is as good */
 #define LZ4D_SCRATCH 256                     /* per-warp shared scratch after the ring: sequence table + start-bit words */
 #define LZ4D_SMEM (LZ4D_RING + LZ4D_SCRATCH)
 
@@ -432,7 +454,84 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
   int ring_lo = 0;                           /* positions [max(ring_lo, op-RING), op) are valid in the ring */
   if (cap == 0) return (csize == 1 && in[0] == 0) ? 0 : -1;   /* lz4.c:2062-2066 */
   if (csize == 0) return -1;
+  int dense_skip = 0, dense_back = 0;
   for (;;) {
+    /* ---- dense path: a run of literal-free sequences, one per lane ----
+     * The byte-planes of shuffled data decode to long chains of 3-byte sequences (token with
+     * 0 literals and a 4..18 byte match, 16-bit offset).  If the sequence at ip is of that form the
+     * next one starts at ip+3, so lane l parses the 3 bytes at ip+3l and the leading run of lanes
+     * that all see this form are real sequences.  A prefix sum of the match lengths gives every
+     * lane its output position; sequences whose source lies entirely before the batch's first
+     * output byte are independent, and every lane copies its own match. */
+    if (dense_skip > 0) dense_skip--;
+    else if (ip + 104 <= iend && op + LZ4D_DENSE_OUT <= oend - LZ4_MFLIMIT) {
+      const u32 w = ldp_win4(ib, ip + 3 * lane);
+      lz4d_prefetch(in, ip + 256 + 128 * lane, lane < 2 ? iend : 0);
+      const u32 token = w & 0xffu;
+      const int off = (int)((w >> 8) & 0xffffu);
+      const unsigned okm = __ballot_sync(FULLMASK, (token >> 4) == 0u && (token & 15u) != 15u);
+      int cnt = okm == FULLMASK ? 32 : __ffs((int)~okm) - 1;
+      const int ml = lane < cnt ? (int)(token & 15u) + 4 : 0;
+      int incl = ml;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULLMASK, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int dst = op + incl - ml, match = dst - off;
+      /* first sequence that reads its own batch's output (or is invalid: off == 0, match < 0) ends the run */
+      const unsigned bad = __ballot_sync(FULLMASK, lane < cnt && (off < incl || match < 0));
+      if (bad) cnt = __ffs((int)bad) - 1;
+      /* the sequence that ends the run is very often a longer literal-free match with one extra
+       * length byte (token 0x0F, offset, len): it is decoded in the same step, by the whole warp */
+      int tlen = 0, toff = 0;
+      if (cnt < 32) {
+        const u32 tw = __shfl_sync(FULLMASK, w, cnt);
+        if ((tw & 0xffu) == 0x0fu && (tw >> 24) != 255u) { tlen = 19 + (int)(tw >> 24); toff = (int)((tw >> 8) & 0xffffu); }
+      }
+      const int total = cnt ? __shfl_sync(FULLMASK, incl, cnt - 1) : 0;
+      const int top = op + total, tmatch = top - toff;
+      if (tlen && (toff == 0 || tmatch < 0 || top + tlen > oend - LZ4_MFLIMIT)) tlen = 0;   /* left to the general path */
+      if (cnt >= LZ4D_DENSE_MIN || tlen) {
+        if (lane < cnt) {
+          if (off <= LZ4D_RING - LZ4D_DENSE_OUT - 64 && match >= ring_lo) {
+            for (int k = 0; k < ml; k++) {
+              const u32 v = smem_ld_u8(ring, (u32)(match + k) & LZ4D_RMASK);
+              out[dst + k] = (u8)v;
+              smem_st_u8(ring, (u32)(dst + k) & LZ4D_RMASK, v);
+            }
+          } else {
+            for (int k = 0; k < ml; k++) {
+              const u32 v = out[match + k];
+              out[dst + k] = (u8)v;
+              smem_st_u8(ring, (u32)(dst + k) & LZ4D_RMASK, v);
+            }
+          }
+        }
+        __syncwarp();
+        ip += 3 * cnt; op = top;
+        LZ4D_DBGN(g_dbg_lz4d_dense_seqs, cnt);
+        if (tlen) {
+          if (toff <= LZ4D_RING - 512 && tmatch >= ring_lo) {
+            for (int k = lane; k < tlen; k += 32) {
+              const u32 v = smem_ld_u8(ring, (u32)(tmatch + (toff >= tlen ? k : k % toff)) & LZ4D_RMASK);
+              out[op + k] = (u8)v;
+              smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
+            }
+          } else {
+            warp_copy_match(out, op, tmatch, tlen);
+            ring_lo = op + tlen;
+          }
+          __syncwarp();
+          ip += 4; op += tlen;
+          LZ4D_DBG(g_dbg_lz4d_dense_seqs);
+        }
+        dense_back = 0;
+        continue;
+      }
+      dense_back = dense_back < 8 ? dense_back + 1 : 8;   /* not that kind of data right here: back off */
+      dense_skip = dense_back;
+    }
     /* ---- batch path: up to 11 short sequences per round ----
      * Lane l speculates that a sequence starts at input byte ip+l and parses it from its own
      * 12-byte window.  Sequences whose offset reaches back past everything this batch can write

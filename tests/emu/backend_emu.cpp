@@ -27,7 +27,7 @@ void emu_set_all_device(int on) { g_all_device = on; }
 unsigned long long emu_collectives(void) { return simt::g_collectives; }
 int emu_last_need(void) { return g_last_need; }
 void emu_set_blz_pack(int on) { g_blz_pack = on; }
-void emu_lz4d_counters(long long* c) { c[0] = g_dbg_lz4d_batch_seqs; c[1] = g_dbg_lz4d_fast_seqs; c[2] = g_dbg_lz4d_general_seqs; }
+void emu_lz4d_counters(long long* c) { c[0] = g_dbg_lz4d_batch_seqs; c[1] = g_dbg_lz4d_fast_seqs; c[2] = g_dbg_lz4d_general_seqs; c[3] = g_dbg_lz4d_dense_seqs; }
 
 int b2_backend_init(void) { return 0; }
 int b2_get_device(void) { return 0; }

@@ -152,16 +152,16 @@ def test_lz4_decoder_paths_are_all_exercised(emu, orc):
     """The batch-parallel, single-sequence and general decode paths must all run (and agree with
     the source) on shuffled bench.c data -- guards against a fast path silently never being taken."""
     import ctypes as C
-    counters = (C.c_longlong * 3)()
+    counters = (C.c_longlong * 4)()
     src = gen("bench", 1 << 20)
     cb, chunk = compress(orc, "orc_compress_ctx", 5, 1, 4, src, len(src) + 16, "lz4")
     emu.emu_lz4d_counters(counters)
     before = list(counters)
     dn, out = decompress(emu, "blosc_decompress_ctx", chunk, len(src))
     emu.emu_lz4d_counters(counters)
-    batch, fast, general = (counters[i] - before[i] for i in range(3))
+    batch, fast, general, dense = (counters[i] - before[i] for i in range(4))
     assert dn == len(src) and (out[:dn] == src).all()
-    assert batch > 10000 and fast > 0 and general > 0, (batch, fast, general)
+    assert dense > 10000 and batch > 100 and fast > 0 and general > 0, (batch, fast, general, dense)
 
 
 def test_pageable_host_staging(emu, orc):
@@ -182,3 +182,40 @@ def test_pageable_host_staging(emu, orc):
         assert dn == len(rnd) and (out[:dn] == rnd).all()
     finally:
         emu.emu_set_all_pinned(1)
+
+
+def test_lz4_dense_path_on_corrupted_chains(emu, orc):
+    """The dense decoder path (32 literal-free sequences per step) on a byte-plane of shuffled
+    bench.c data: same accept/reject verdict and same bytes as the oracle when single bytes of the
+    stream are damaged (offsets reaching before the block, overlapping sources, broken tokens)."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    words = gen("bench", 1 << 19).view(np.uint32)
+    n = len(words)
+    best = (0, None, None)
+    for b in range(3):                                         # the chain-heavy byte-plane of the shuffle
+        pl = ((words >> (8 * b)) & 0xff).astype(np.uint8)
+        buf = np.zeros(n + 64, np.uint8)
+        r = orc.orc_lz4_compress_fast(ptr(pl), ptr(buf), ci(n), ci(n), ci(5))
+        if r > best[0]:
+            best = (r, pl, buf)
+    ra, plane, a = best
+    assert 0 < ra < n // 2
+    counters = (C.c_longlong * 4)()
+    emu.emu_lz4d_counters(counters)
+    dense0 = counters[3]
+    o = np.zeros(n + 8, np.uint8)
+    assert emu.emu_lz4_decode(ptr(a), ci(ra), ptr(o), ci(n)) == n and (o[:n] == plane).all()
+    emu.emu_lz4d_counters(counters)
+    assert counters[3] - dense0 > 5000
+    for trial in range(120):
+        c = a[:ra].copy()
+        for pos in rng.integers(0, ra, 1 + trial % 3):
+            kind = trial % 4
+            c[pos] = (0, 0xF0, 0x0F, int(rng.integers(0, 256)))[kind]
+        o1 = np.zeros(n + 8, np.uint8); o2 = np.zeros(n + 8, np.uint8)
+        d1 = orc.orc_lz4_decompress_safe(ptr(c), ptr(o1), ci(ra), ci(n))
+        d2 = emu.emu_lz4_decode(ptr(c), ci(ra), ptr(o2), ci(n))
+        assert (d1 < 0) == (d2 < 0), (trial, d1, d2)
+        if d1 >= 0:
+            assert d1 == d2 and (o1[:d1] == o2[:d1]).all() and (o2[n:] == 0).all(), trial

@@ -53,6 +53,7 @@ typedef u8* smem_addr_t;
 DEV smem_addr_t smem_addr(void* p) { return (u8*)p; }
 DEV u32 smem_ld_u8(smem_addr_t base, u32 off) { return base[off]; }
 DEV void smem_st_u8(smem_addr_t base, u32 off, u32 v) { base[off] = (u8)v; }
+DEV u32 smem_ld_u32(smem_addr_t base, u32 off) { u32 v; memcpy(&v, base + off, 4); return v; }   /* off % 4 == 0 */
 #else
 typedef u32 smem_addr_t;
 DEV smem_addr_t smem_addr(void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -63,6 +64,11 @@ DEV u32 smem_ld_u8(smem_addr_t base, u32 off) {
 }
 DEV void smem_st_u8(smem_addr_t base, u32 off, u32 v) {
   asm volatile("st.shared.u8 [%0], %1;" :: "r"(base + off), "r"(v) : "memory");
+}
+DEV u32 smem_ld_u32(smem_addr_t base, u32 off) {                 /* off % 4 == 0 */
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + off));
+  return v;
 }
 #endif
 

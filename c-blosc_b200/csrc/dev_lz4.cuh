@@ -493,18 +493,26 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       const int top = op + total, tmatch = top - toff;
       if (tlen && (toff == 0 || tmatch < 0 || top + tlen > oend - LZ4_MFLIMIT)) tlen = 0;   /* left to the general path */
       if (cnt >= LZ4D_DENSE_MIN || tlen) {
-        if (lane < cnt) {
-          if (off <= LZ4D_RING - LZ4D_DENSE_OUT - 64 && match >= ring_lo) {
-            for (int k = 0; k < ml; k++) {
-              const u32 v = smem_ld_u8(ring, (u32)(match + k) & LZ4D_RMASK);
-              out[dst + k] = (u8)v;
-              smem_st_u8(ring, (u32)(dst + k) & LZ4D_RMASK, v);
-            }
-          } else {
-            for (int k = 0; k < ml; k++) {
-              const u32 v = out[match + k];
-              out[dst + k] = (u8)v;
-              smem_st_u8(ring, (u32)(dst + k) & LZ4D_RMASK, v);
+        {
+          /* every lane copies its own match, 4 source bytes per step: from the ring (two aligned
+           * words + funnel shift) or, for far offsets, from the output in global memory */
+          const int mlmax = __ballot_sync(FULLMASK, ml > 16) ? 18 : (__ballot_sync(FULLMASK, ml > 8) ? 16 : 8);
+          const bool from_ring = off <= LZ4D_RING - LZ4D_DENSE_OUT - 64 && match >= ring_lo;
+          u8* o = out + dst;
+#pragma unroll 1
+          for (int k = 0; k < mlmax; k += 4) {
+            if (k < ml) {
+              u32 v;
+              if (from_ring) {
+                const u32 m = (u32)(match + k);
+                v = __funnelshift_r(smem_ld_u32(ring, m & (LZ4D_RMASK & ~3u)), smem_ld_u32(ring, (m + 4u) & (LZ4D_RMASK & ~3u)), (m & 3u) * 8u);
+              } else v = ld_u32(out + match + k);       /* may read a few bytes past the source: they are not used */
+              const int nb = ml - k;
+              const u32 r = (u32)(dst + k);
+              o[k] = (u8)v; smem_st_u8(ring, r & LZ4D_RMASK, v);
+              if (nb > 1) { o[k + 1] = (u8)(v >> 8); smem_st_u8(ring, (r + 1u) & LZ4D_RMASK, v >> 8); }
+              if (nb > 2) { o[k + 2] = (u8)(v >> 16); smem_st_u8(ring, (r + 2u) & LZ4D_RMASK, v >> 16); }
+              if (nb > 3) { o[k + 3] = (u8)(v >> 24); smem_st_u8(ring, (r + 3u) & LZ4D_RMASK, v >> 24); }
             }
           }
         }
@@ -512,15 +520,12 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
         ip += 3 * cnt; op = top;
         LZ4D_DBGN(g_dbg_lz4d_dense_seqs, cnt);
         if (tlen) {
-          if (toff <= LZ4D_RING - 512 && tmatch >= ring_lo) {
-            for (int k = lane; k < tlen; k += 32) {
-              const u32 v = smem_ld_u8(ring, (u32)(tmatch + (toff >= tlen ? k : k % toff)) & LZ4D_RMASK);
-              out[op + k] = (u8)v;
-              smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
-            }
-          } else {
-            warp_copy_match(out, op, tmatch, tlen);
-            ring_lo = op + tlen;
+          const bool from_ring = toff <= LZ4D_RING - 512 && tmatch >= ring_lo;
+          for (int k = lane; k < tlen; k += 32) {             /* sources are all before `op`: no lane waits for another */
+            const int src = tmatch + (toff >= tlen ? k : k % toff);
+            const u32 v = from_ring ? smem_ld_u8(ring, (u32)src & LZ4D_RMASK) : (u32)out[src];
+            out[op + k] = (u8)v;
+            smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
           }
           __syncwarp();
           ip += 4; op += tlen;
@@ -689,12 +694,16 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
     cpy = op + len;
     if (cpy > oend - LZ4_LASTLITERALS) return -1;             /* lz4.c:2423 */
     __syncwarp();                                             /* earlier output must be visible to all lanes */
-    if (len <= 2048 && off <= LZ4D_RING - 2048 - 64 && match >= ring_lo) {
-      /* sources are all inside the ring and are not overwritten by this copy */
+    if (len <= 2048) {
+      /* sources lie before `op`; inside the ring they are not overwritten by this copy.  Far
+       * sources are read from global memory, but the output still goes into the ring so that it
+       * stays a mirror of the last 16 KiB */
+      const bool from_ring = off <= LZ4D_RING - 2048 - 64 && match >= ring_lo;
       for (int k0 = 0; k0 < len; k0 += 32) {
         const int k = k0 + lane;
         if (k < len) {
-          const u32 v = smem_ld_u8(ring, (u32)(match + (off >= len ? k : k % off)) & LZ4D_RMASK);
+          const int src = match + (off >= len ? k : k % off);
+          const u32 v = from_ring ? smem_ld_u8(ring, (u32)src & LZ4D_RMASK) : (u32)out[src];
           out[op + k] = (u8)v;
           smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
         }

@@ -112,6 +112,23 @@ DEV u32 lz4_hash_seq(u32 lo, u32 b4) {                        /* lz4.c:777-806 o
   return (u32)(((seq << 24) * 889523592379ull) >> (64 - 12));
 }
 
+/* LZ4_count continuation for matches that outgrow the scalar compares: first round 4 bytes per
+ * lane (128 bytes, two loads per lane), only then the 512-bytes-per-round loop.  p > q, `n` =
+ * stream length, limit = matchlimit. */
+DEV int lz4_count_tail(const StreamBase& sb, const u8* __restrict__ s, int p, int q, int limit, int n) {
+  if (p + 136 <= n) {                                           /* p + 128 <= limit and the loads stay inside the stream */
+    const int lane = lane_id();
+    const u32 x = ldp_win4(sb, p + 4 * lane) ^ ldp_win4(sb, q + 4 * lane);
+    const unsigned full = __ballot_sync(FULLMASK, x == 0u);
+    if (full != FULLMASK) {
+      const int fl = __ffs((int)~full) - 1;
+      return fl * 4 + eq_bytes32(__shfl_sync(FULLMASK, x, fl));
+    }
+    return 128 + warp_count_match(s, p + 128, q + 128, limit);
+  }
+  return warp_count_match(s, p, q, limit);
+}
+
 /* Returns the compressed size, or 0 when the stream does not fit in `cap`
  * (LZ4_compress_fast's limitedOutput failure).  Uniform across the warp.
  * `tabmem` is LZ4_TABLE_BYTES of shared memory private to this warp.
@@ -156,14 +173,16 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   int nrec = 0, recop = 0;
   u32 rec = 0;
 #define LZ4_FLUSH_CHECKED() do { if (nrec) { LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS)); } LZ4_FLUSH(); } while (0)
-#define LZ4_FLUSH() do { if (lane < nrec) { d[recop] = (u8)rec; d[recop + 1] = (u8)(rec >> 8); d[recop + 2] = (u8)(rec >> 16); } nrec = 0; } while (0)
+#define LZ4_FLUSH() do { if (lane < nrec) { d[recop] = (u8)rec; d[recop + 1] = (u8)(rec >> 8); d[recop + 2] = (u8)(rec >> 16); \
+                                             if ((rec & 15u) == 15u) d[recop + 3] = (u8)(rec >> 24); } nrec = 0; } while (0)
 
   if (n >= LZ4_MFLIMIT + 1) {                 /* lz4.c:1002 */
     bool post = false;                        /* true: a match just ended at ip (== anchor) */
     for (;;) {
       int match = 0, lit = 0, back = 0;
       u32 ipn = 0, cn = 0;                    /* bytes [ip+4, ip+8) and [match+4, match+8) of the hit */
-      bool have_next = false, hit = false, imm = false;
+      bool have_next = false, hit = false, imm = false, have_mc = false;
+      int mc_carry = 0;
 
       if (post && ip + 64 <= n) {
         /* ---- chained "test next position" on the lane-cached window ---- */
@@ -199,23 +218,26 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
               const u32 x3 = p3 ^ q3, x4 = p4 ^ q4;
               if (x3) mc = 8 + eq_bytes32(x3);
               else if (x4) mc = 12 + eq_bytes32(x4);
-              else mc = 16 + warp_count_match(s, ip + 20, cand + 20, matchlimit);   /* ip+64 <= n: far from matchlimit */
+              else mc = 16 + lz4_count_tail(sb, s, ip + 20, cand + 20, matchlimit, n);   /* ip+64 <= n: far from matchlimit */
             }
             const int off = ip - cand;
-            if (mc < 15) {
-              /* lz4.c:1187-1211 with 0 literals asks for op + 9 <= olimit; op only grows inside a chain,
-               * so the check is made once per parked batch, before anything is written (LZ4_FLUSH_CHECKED) */
-              if (lane == nrec) { rec = (u32)mc | ((u32)off << 8); recop = op; }
+            if (mc < 15 + 255) {
+              /* lz4.c:1187-1226 with 0 literals: token, offset and -- from 19 bytes on -- one length byte.
+               * Both limitedOutput checks of such a sequence ask for (op after it) + 6 <= olimit; op only
+               * grows inside a chain, so the check is made once per parked batch, before anything is
+               * written (LZ4_FLUSH_CHECKED) */
+              const bool ext = mc >= 15;
+              if (lane == nrec) { rec = (ext ? 15u | ((u32)(mc - 15) << 24) : (u32)mc) | ((u32)off << 8); recop = op; }
               nrec++;
-              op += 3;
+              op += ext ? 4 : 3;
               if (nrec == 32) LZ4_FLUSH_CHECKED();
               ip += mc + 4;
               anchor = ip;
               if (ip >= mfl1) break;                                         /* lz4.c:1230-1233 */
               chained = true;
-            } else {                                                         /* long match: general emission below */
+            } else {                                                         /* very long match: general emission below */
               hit = true; imm = true; match = cand;
-              ipn = n4; cn = c1; have_next = true;
+              have_mc = true; mc_carry = mc;
             }
           }
         }
@@ -327,7 +349,8 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
        * Most matches of shuffled data are 8..20 bytes long: compare that much with scalar
        * (warp-uniform) loads first and only then fall into the 512-bytes-per-round warp loop. ---- */
       int mc;
-      {
+      if (have_mc) mc = mc_carry;                                    /* already counted by the chained probe */
+      else {
         const int room = matchlimit - (ip + 4);                      /* >= 3 because ip < mflimitPlusOne */
         if (have_next) {
           const u32 x = ipn ^ cn;
@@ -340,7 +363,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
             if (x0) mc = 4 + eq_bytes32(x0);
             else if (x1) mc = 8 + eq_bytes32(x1);
             else if (x2) mc = 12 + eq_bytes32(x2);
-            else mc = 16 + warp_count_match(s, ip + 20, match + 20, matchlimit);
+            else mc = 16 + lz4_count_tail(sb, s, ip + 20, match + 20, matchlimit, n);
           } else mc = 4 + (room > 4 ? warp_count_match(s, ip + 8, match + 8, matchlimit) : 0);
           if (mc > room) mc = room;
         } else mc = warp_count_match(s, ip + 4, match + 4, matchlimit);

@@ -34,6 +34,8 @@ DEV u32 lz4_hash_at(const u8* __restrict__ s, int pos) {       /* lz4.c:777-806 
   return (u32)(((seq << 24) * 889523592379ull) >> (64 - 12));
 }
 
+#define LZ4_SCALAR_PROBES 4     /* probes done one at a time before the 32-wide rounds (must be <= 64) */
+
 /* Offset from the search start of the it-th probe of the skip schedule
  * (lz4.c:1043-1053): steps are 1, then accel + (k >> 6) for k = 0,1,2,... */
 DEV long long lz4_probe_offset(int it, int accel) {
@@ -164,12 +166,12 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
   /* first byte (lz4.c:1005-1010): table[hash(0)] = 0, which the zeroed table already says */
 
   /* Lane-cached window for the literal-free chains that dominate shuffled data: lane l keeps the
-   * 8 bytes at position w0+l and their hash, so the "fill table at ip-2 / test ip" step
+   * 12 bytes at position w0+l and their hash, so the "fill table at ip-2 / test ip" step
    * (lz4.c:1236-1294) fetches both hashes and the bytes to compare with shuffles instead of
-   * reloading and re-hashing; a refill costs one round of loads per ~2 sequences.  The 3-byte
+   * reloading and re-hashing; a refill costs one round of loads per 2-3 sequences.  The 3-byte
    * sequences such a chain produces (token, offset) are parked one per lane and written together. */
   int w0 = -(1 << 30);
-  u32 wq0 = 0, wq1 = 0, wh = 0;
+  u32 wq0 = 0, wq1 = 0, wq2 = 0, wh = 0;
   int nrec = 0, recop = 0;
   u32 rec = 0;
 #define LZ4_FLUSH_CHECKED() do { if (nrec) { LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS)); } LZ4_FLUSH(); } while (0)
@@ -186,17 +188,18 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
 
       if (post && ip + 64 <= n) {
         /* ---- chained "test next position" on the lane-cached window ---- */
-        if (ip - 2 < w0 || ip > w0 + 23) {
+        if (ip - 2 < w0 || ip > w0 + 31) {
           w0 = ip - 2;
-          ldp_win8(sb, w0 + lane, wq0, wq1);
+          ldp_win12(sb, w0 + lane, wq0, wq1, wq2);                         /* reaches byte w0+46 < ip+64 <= n */
+          lz4d_prefetch(s, w0 + 192, lane == 0 ? n : 0);                   /* the line a few refills ahead */
           wh = lz4_hash_seq<U16>(wq0, wq1);
         }
-        const int li = ip - w0;                                            /* 2 .. 23 */
+        const int li = ip - w0;                                            /* 2 .. 31 */
         const u32 h2 = __shfl_sync(FULLMASK, wh, li - 2);
         const u32 h = __shfl_sync(FULLMASK, wh, li);
         const u32 seq = __shfl_sync(FULLMASK, wq0, li);
         const u32 n4 = __shfl_sync(FULLMASK, wq1, li);                     /* bytes ip+4 .. ip+7 */
-        const u32 n8 = __shfl_sync(FULLMASK, wq0, li + 8);                 /* bytes ip+8 .. ip+11 */
+        const u32 n8 = __shfl_sync(FULLMASK, wq2, li);                     /* bytes ip+8 .. ip+11 */
         if (lane == 0) LZ4_TPUT(h2, ip - 2);
         __syncwarp();
         const int cand = LZ4_TGET(h);
@@ -271,9 +274,9 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       if (!hit) {
         /* ---- find a match (lz4.c:1043-1101): two scalar probes, then 32-wide rounds ---- */
         bool ended = false;
-        for (int it = 0; it < 2; it++) {
-          const int pos = ip + (it ? 1 : 0);                               /* probe offsets 0, 1 */
-          if (ip + (it ? 1 + accel : 1) > mfl1) { ended = true; break; }   /* `goto _last_literals` (lz4.c:1055) */
+        for (int it = 0; it < LZ4_SCALAR_PROBES; it++) {
+          const int pos = ip + (it ? 1 + (it - 1) * accel : 0);            /* probe offsets 0, 1, 1+accel, 1+2*accel (lz4.c:1043-1053) */
+          if (ip + 1 + it * accel > mfl1) { ended = true; break; }         /* `goto _last_literals` (lz4.c:1055) */
           u32 b0, b1 = 0, b2 = 0;
           const bool wide = pos + 16 <= n;
           if (wide) ldp_win12(sb, pos, b0, b1, b2);
@@ -295,7 +298,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
         }
         if (!hit && !ended) {
           __syncwarp();
-          for (int base_it = 2;; base_it += 32) {
+          for (int base_it = LZ4_SCALAR_PROBES;; base_it += 32) {
             const int itl = base_it + lane;
             const bool valid = ip + lz4_probe_offset(itl + 1, accel) <= mfl1;
             const int pos = valid ? ip + (int)lz4_probe_offset(itl, accel) : 0;

@@ -187,65 +187,67 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       int mc_carry = 0;
 
       if (post && ip + 64 <= n) {
-        /* ---- chained "test next position" on the lane-cached window ---- */
-        if (ip - 2 < w0 || ip > w0 + 31) {
-          w0 = ip - 2;
-          ldp_win12(sb, w0 + lane, wq0, wq1, wq2);                         /* reaches byte w0+46 < ip+64 <= n */
-          lz4d_prefetch(s, w0 + 192, lane == 0 ? n : 0);                   /* the line a few refills ahead */
-          wh = lz4_hash_seq<U16>(wq0, wq1);
-        }
-        const int li = ip - w0;                                            /* 2 .. 31 */
-        const u32 h2 = __shfl_sync(FULLMASK, wh, li - 2);
-        const u32 h = __shfl_sync(FULLMASK, wh, li);
-        const u32 seq = __shfl_sync(FULLMASK, wq0, li);
-        const u32 n4 = __shfl_sync(FULLMASK, wq1, li);                     /* bytes ip+4 .. ip+7 */
-        const u32 n8 = __shfl_sync(FULLMASK, wq2, li);                     /* bytes ip+8 .. ip+11 */
-        if (lane == 0) LZ4_TPUT(h2, ip - 2);
-        __syncwarp();
-        const int cand = LZ4_TGET(h);
-        __syncwarp();                      /* every lane has read the old entry before lane 0 overwrites it */
-        if (lane == 0) LZ4_TPUT(h, ip);
-        bool chained = false;
-        if (U16 || cand + 65535 >= ip) {
-          u32 c0, c1, c2;
-          ldp_win12(sb, cand, c0, c1, c2);
-          if (c0 == seq) {
-            int mc;
-            const u32 x1 = n4 ^ c1, x2 = n8 ^ c2;
-            if (x1) mc = eq_bytes32(x1);
-            else if (x2) mc = 4 + eq_bytes32(x2);
-            else {                                                            /* >= 12 bytes: next 8 from memory */
-              u32 p3, p4, q3, q4;
-              ldp_win8(sb, ip + 12, p3, p4);
-              ldp_win8(sb, cand + 12, q3, q4);
-              const u32 x3 = p3 ^ q3, x4 = p4 ^ q4;
-              if (x3) mc = 8 + eq_bytes32(x3);
-              else if (x4) mc = 12 + eq_bytes32(x4);
-              else mc = 16 + lz4_count_tail(sb, s, ip + 20, cand + 20, matchlimit, n);   /* ip+64 <= n: far from matchlimit */
-            }
-            const int off = ip - cand;
-            if (mc < 15 + 255) {
-              /* lz4.c:1187-1226 with 0 literals: token, offset and -- from 19 bytes on -- one length byte.
-               * Both limitedOutput checks of such a sequence ask for (op after it) + 6 <= olimit; op only
-               * grows inside a chain, so the check is made once per parked batch, before anything is
-               * written (LZ4_FLUSH_CHECKED) */
-              const bool ext = mc >= 15;
-              if (lane == nrec) { rec = (ext ? 15u | ((u32)(mc - 15) << 24) : (u32)mc) | ((u32)off << 8); recop = op; }
-              nrec++;
-              op += ext ? 4 : 3;
-              if (nrec == 32) LZ4_FLUSH_CHECKED();
-              ip += mc + 4;
-              anchor = ip;
-              if (ip >= mfl1) break;                                         /* lz4.c:1230-1233 */
-              chained = true;
-            } else {                                                         /* very long match: general emission below */
-              hit = true; imm = true; match = cand;
-              have_mc = true; mc_carry = mc;
-            }
+        /* ---- chained "test next position" on the lane-cached window: stays in this loop for as
+         * long as every match is immediately followed by another one ---- */
+        bool room = true;
+        for (;;) {
+          if (ip - 2 < w0 || ip > w0 + 31) {
+            if (nrec >= 24) LZ4_FLUSH_CHECKED();                             /* a window serves at most 8 sequences */
+            w0 = ip - 2;
+            ldp_win12(sb, w0 + lane, wq0, wq1, wq2);                         /* reaches byte w0+46 < ip+64 <= n */
+            lz4d_prefetch(s, w0 + 192, lane == 0 ? n : 0);                   /* the line a few refills ahead */
+            wh = lz4_hash_seq<U16>(wq0, wq1);
           }
+          const int li = ip - w0;                                            /* 2 .. 31 */
+          const u32 h2 = __shfl_sync(FULLMASK, wh, li - 2);
+          const u32 h = __shfl_sync(FULLMASK, wh, li);
+          const u32 seq = __shfl_sync(FULLMASK, wq0, li);
+          const u32 n4 = __shfl_sync(FULLMASK, wq1, li);                     /* bytes ip+4 .. ip+7 */
+          const u32 n8 = __shfl_sync(FULLMASK, wq2, li);                     /* bytes ip+8 .. ip+11 */
+          if (lane == 0) LZ4_TPUT(h2, ip - 2);
+          __syncwarp();
+          const int cand = LZ4_TGET(h);
+          __syncwarp();                    /* every lane has read the old entry before lane 0 overwrites it */
+          if (lane == 0) LZ4_TPUT(h, ip);
+          u32 c0, c1, c2;
+          ldp_win12(sb, cand, c0, c1, c2);   /* cand is a position < ip whatever the table holds: safe even when it is too far back */
+          if (!((U16 || cand + 65535 >= ip) && c0 == seq)) { ip++; break; }  /* lz4.c:1298; on to the search below */
+          int mc;
+          const u32 x1 = n4 ^ c1, x2 = n8 ^ c2;
+          if (x1 | x2) {
+            const u32 xx = x1 ? x1 : x2;
+            mc = ((__ffs((int)xx) - 1) >> 3) + (x1 ? 0 : 4);
+          } else {                                                           /* >= 12 bytes: next 8 from memory */
+            u32 p3, p4, q3, q4;
+            ldp_win8(sb, ip + 12, p3, p4);
+            ldp_win8(sb, cand + 12, q3, q4);
+            const u32 x3 = p3 ^ q3, x4 = p4 ^ q4;
+            if (x3) mc = 8 + eq_bytes32(x3);
+            else if (x4) mc = 12 + eq_bytes32(x4);
+            else mc = 16 + lz4_count_tail(sb, s, ip + 20, cand + 20, matchlimit, n);   /* ip+64 <= n: far from matchlimit */
+          }
+          if (mc >= 15 + 255) {                                              /* very long match: general emission below */
+            hit = true; imm = true; match = cand;
+            have_mc = true; mc_carry = mc;
+            break;
+          }
+          /* lz4.c:1187-1226 with 0 literals: token, offset and -- from 19 bytes on -- one length byte.
+           * Both limitedOutput checks of such a sequence ask for (op after it) + 6 <= olimit; op only
+           * grows inside a chain, so the check is made once per parked batch, before anything is
+           * written (LZ4_FLUSH_CHECKED) */
+          const bool ext = mc >= 15;
+          const int off = ip - cand;
+          if (lane == nrec) { rec = (ext ? 15u | ((u32)(mc - 15) << 24) : (u32)mc) | ((u32)off << 8); recop = op; }
+          nrec++;
+          op += ext ? 4 : 3;
+          ip += mc + 4;
+          anchor = ip;
+          if (ip + 64 > n) { room = false; break; }
         }
-        if (chained) continue;
-        if (!hit) ip++;                                                      /* lz4.c:1298 */
+        if (!room) {                                                         /* a match ended close to the end of the stream */
+          if (ip >= mfl1) break;                                             /* lz4.c:1230-1233 */
+          continue;                                                          /* post stays true: the plain probe below takes over */
+        }
       } else if (post) {
         /* ---- fill table at ip-2, test position ip (lz4.c:1236-1294); no literals on a hit ---- */
         u32 b0, b1, b2 = 0;

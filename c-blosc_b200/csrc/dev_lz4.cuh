@@ -74,6 +74,24 @@ DEV void ldp_win12(const StreamBase& sb, int p, u32& b0, u32& b1, u32& b2) {
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh); b2 = __funnelshift_r(w2, w3, sh);
 #endif
 }
+/* The same in two steps, for loads that are requested long before their bytes are needed:
+ * ldp_raw12 only issues the aligned word loads, ldp_take12 aligns them (first use of the data). */
+DEV void ldp_raw12(const StreamBase& sb, int p, u32& r0, u32& r1, u32& r2, u32& r3) {
+#ifdef SIMT_EMU
+  memcpy(&r0, sb.s + p, 4); memcpy(&r1, sb.s + p + 4, 4); memcpy(&r2, sb.s + p + 8, 4); r3 = 0;
+#else
+  const u32* w = sb.s32 + ((p + sb.sal) >> 2);
+  r0 = __ldg(w); r1 = __ldg(w + 1); r2 = __ldg(w + 2); r3 = __ldg(w + 3);
+#endif
+}
+DEV void ldp_take12(const StreamBase& sb, int p, u32 r0, u32 r1, u32 r2, u32 r3, u32& b0, u32& b1, u32& b2) {
+#ifdef SIMT_EMU
+  (void)sb; (void)p; (void)r3; b0 = r0; b1 = r1; b2 = r2;
+#else
+  const u32 sh = (u32)((p + sb.sal) & 3) * 8u;
+  b0 = __funnelshift_r(r0, r1, sh); b1 = __funnelshift_r(r1, r2, sh); b2 = __funnelshift_r(r2, r3, sh);
+#endif
+}
 /* 8 bytes at position p; touches at most byte p+11 */
 DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
 #ifdef SIMT_EMU
@@ -172,6 +190,8 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
    * sequences such a chain produces (token, offset) are parked one per lane and written together. */
   int w0 = -(1 << 30);
   u32 wq0 = 0, wq1 = 0, wq2 = 0, wh = 0;
+  int pb = -(1 << 30);                       /* base of the window requested ahead of time */
+  u32 pq0 = 0, pq1 = 0, pq2 = 0, pq3 = 0;    /* its raw aligned words */
   int nrec = 0, recop = 0;
   u32 rec = 0;
 #define LZ4_FLUSH_CHECKED() do { if (nrec) { LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS)); } LZ4_FLUSH(); } while (0)
@@ -193,10 +213,16 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
         for (;;) {
           if (ip - 2 < w0 || ip > w0 + 31) {
             if (nrec >= 24) LZ4_FLUSH_CHECKED();                             /* a window serves at most 8 sequences */
-            w0 = ip - 2;
-            ldp_win12(sb, w0 + lane, wq0, wq1, wq2);                         /* reaches byte w0+46 < ip+64 <= n */
-            lz4d_prefetch(s, w0 + 192, lane == 0 ? n : 0);                   /* the line a few refills ahead */
+            /* The window that follows (base w0+30: the first ip past this window is >= w0+32) was
+             * requested at the previous refill, so its bytes are here by now; only a long match
+             * that jumps over it pays for a blocking load. */
+            if (ip - 2 >= pb && ip <= pb + 31) { w0 = pb; ldp_take12(sb, w0 + lane, pq0, pq1, pq2, pq3, wq0, wq1, wq2); }
+            else { w0 = ip - 2; ldp_win12(sb, w0 + lane, wq0, wq1, wq2); }   /* reaches byte w0+46 < ip+64 <= n */
             wh = lz4_hash_seq<U16>(wq0, wq1);
+            pb = w0 + 30;
+            if (pb + 31 + 16 <= n) ldp_raw12(sb, pb + lane, pq0, pq1, pq2, pq3);   /* not waited for */
+            else pb = -(1 << 30);
+            lz4d_prefetch(s, w0 + 192, lane == 0 ? n : 0);                   /* the line a few refills ahead */
           }
           const int li = ip - w0;                                            /* 2 .. 31 */
           const u32 h2 = __shfl_sync(FULLMASK, wh, li - 2);

@@ -50,7 +50,7 @@ def bench_words(nbytes, np):
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of one encode_kernel launch, from the committed
     `ncu --set full` summary (profiles/); None when no capture exists for this workload."""
-    name = {"lz4-shuffle-ts4-cl5-256MiB": "r1_ncu_lz4_cfg2_v7.json"}.get(workload)
+    name = {"lz4-shuffle-ts4-cl5-256MiB": "r1_ncu_lz4_cfg2_v16.json"}.get(workload)
     p = os.path.join(ROOT, "profiles", name) if name else None
     if p and os.path.exists(p):
         try:

@@ -219,3 +219,19 @@ def test_lz4_dense_path_on_corrupted_chains(emu, orc):
         assert (d1 < 0) == (d2 < 0), (trial, d1, d2)
         if d1 >= 0:
             assert d1 == d2 and (o1[:d1] == o2[:d1]).all() and (o2[n:] == 0).all(), trial
+
+
+def test_lz4_decode_unaligned_destination(emu, orc):
+    """The decoder stages output in its shared-memory ring and flushes it with 16-byte stores:
+    destinations at every phase of a 16-byte line, nothing written outside [dst, dst+n)."""
+    import ctypes as C
+    for kind, n in (("bench", 70001), ("text", 30011), ("i32", 9000), ("zeros", 5000)):
+        src = gen(kind, n, seed=3) if kind != "bench" else (gen("bench", 4 * n).view(np.uint32)[:n] >> 8).astype(np.uint8)
+        a = np.zeros(n + 64, np.uint8)
+        ra = orc.orc_lz4_compress_fast(ptr(src), ptr(a), ci(n), ci(n + 64), ci(1))
+        assert ra > 0
+        for shift in (1, 4, 7, 8, 13, 15):
+            buf = np.full(n + 64, 0x5A, np.uint8)
+            dst = C.c_void_p(buf.ctypes.data + shift)
+            assert emu.emu_lz4_decode(ptr(a), ci(ra), dst, ci(n)) == n
+            assert (buf[shift:shift + n] == src).all() and (buf[:shift] == 0x5A).all() and (buf[shift + n:] == 0x5A).all()

@@ -57,7 +57,9 @@ extern "C" int b2_set_device(int dev) { CK(cudaSetDevice(dev)); return 0; }
 
 extern "C" int b2_stream_create(b2_stream_t* s) {
   b2_stream_s* st = new b2_stream_s;
-  if (cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking) != cudaSuccess) { delete st; return -1; }
+  /* a blocking stream: like cudaMemcpy, a call is ordered after whatever the caller has already queued on
+   * the legacy default stream (where e.g. PyTorch produces the buffers it hands in) */
+  if (cudaStreamCreateWithFlags(&st->s, cudaStreamDefault) != cudaSuccess) { delete st; return -1; }
   *s = st;
   return 0;
 }

@@ -32,8 +32,12 @@ def byte_ranges(total_bytes: int, chunk_bytes: int, world: int):
 
 
 def _wait(reqs):
+    """Complete P2P requests.  With NCCL, wait() only orders the current CUDA stream after the
+    transfer; the library runs on its own streams, so the host waits for the data here."""
     for q in reqs:
         q.wait()
+    if reqs and torch.cuda.is_available() and torch.cuda.is_initialized():
+        torch.cuda.current_stream().synchronize()
 
 
 def scatter_bytes(dist, full, ranges, rank, device):

@@ -175,6 +175,25 @@ def test_device_resident_round_trip(pkg, orc, cuda):
         assert torch.equal(d_item, d_src[1000 * ts:1000 * ts + 4096])
 
 
+def test_ordered_after_default_stream_work(pkg, orc, cuda):
+    """Like cudaMemcpy, a call is ordered after work the caller has queued on the (legacy) default
+    stream: a buffer still being produced by PyTorch kernels is compressed correctly, and PyTorch
+    work queued right after a call sees its result."""
+    torch = cuda
+    n = 32 << 20
+    x = torch.arange(n // 4, device="cuda", dtype=torch.int32)
+    for _ in range(40):                                   # a queue of kernels the host does not wait for
+        x = (x * 3 + 1) & 0xFFFFF
+    d_chunk = torch.empty(n + 16, dtype=torch.uint8, device="cuda")
+    cb = pkg.compress_ctx(5, 1, 4, n, x, d_chunk, n + 16, "lz4")
+    src = x.cpu().numpy().view(np.uint8)
+    want_n, want = compress(orc, "orc_compress_ctx", 5, 1, 4, src, n + 16, "lz4")
+    assert cb == want_n and (d_chunk[:cb].cpu().numpy() == want[:cb]).all()
+    d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert pkg.decompress_ctx(d_chunk, d_out, n) == n
+    assert torch.equal(d_out.view(torch.int32) + 1, x + 1)
+
+
 def test_corrupted_chunks_fail_cleanly(pkg, cuda):
     """Appendix B of SURVEY.md / tests/fuzz: malformed input returns an error, never crashes."""
     n = 1 << 20

@@ -483,7 +483,7 @@ static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d
 #define LZ4D_RING 16384                      /* bytes of recent output mirrored in shared memory, per warp */
 #define LZ4D_RMASK (LZ4D_RING - 1)
 #define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 26) */
-#define LZ4D_DENSE_OUT 640                   /* a dense batch writes <= 32 x 18 bytes */
+#define LZ4D_DENSE_OUT 1664                  /* a dense step writes <= 28 x 18 + 4 x 273 bytes */
 #define LZ4D_DENSE_MIN 4                     /* fewer chained 3-byte sequences than this: the 11-wide batch path is as good */
 #define LZ4D_SCRATCH 256                     /* per-warp shared scratch after the ring: sequence table + start-bit words */
 #define LZ4D_SMEM (LZ4D_RING + LZ4D_SCRATCH)
@@ -518,14 +518,31 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
      * lane its output position; sequences whose source lies entirely before the batch's first
      * output byte are independent, and every lane copies its own match. */
     if (dense_skip > 0) dense_skip--;
-    else if (ip + 104 <= iend && op + LZ4D_DENSE_OUT <= oend - LZ4_MFLIMIT) {
-      const u32 w = ldp_win4(ib, ip + 3 * lane);
+    else if (ip + 112 <= iend && op + LZ4D_DENSE_OUT <= oend - LZ4_MFLIMIT) {
+      u32 b0, b1;
+      ldp_win8(ib, ip + 3 * lane, b0, b1);                    /* bytes ip+3l .. ip+3l+7 (touches < ip+105) */
       lz4d_prefetch(in, ip + 256 + 128 * lane, lane < 2 ? iend : 0);
-      const u32 token = w & 0xffu;
-      const int off = (int)((w >> 8) & 0xffffu);
-      const unsigned okm = __ballot_sync(FULLMASK, (token >> 4) == 0u && (token & 15u) != 15u);
-      int cnt = okm == FULLMASK ? 32 : __ffs((int)~okm) - 1;
-      const int ml = lane < cnt ? (int)(token & 15u) + 4 : 0;
+      /* Segments: lanes [c, e) see 3-byte sequences at byte shift s; the sequence that ends a
+       * segment is very often a longer literal-free match with one extra length byte (token 0x0F,
+       * offset, len): lane e takes it and the next segment starts one byte later (shift s+1). */
+      int kind = 0, ml = 0, off = 0, c = 0, sft = 0;
+      u32 w = b0;
+      for (;;) {
+        const u32 tok = w & 0xffu;
+        const unsigned okm = __ballot_sync(FULLMASK, lane >= c && (tok >> 4) == 0u && (tok & 15u) != 15u);
+        const unsigned stop = ~okm & ~((1u << c) - 1u);        /* first lane >= c that is not such a sequence */
+        const int e = stop ? __ffs((int)stop) - 1 : 32;
+        if (lane >= c && lane < e) { kind = 1; ml = (int)(tok & 15u) + 4; off = (int)((w >> 8) & 0xffffu); }
+        c = e;
+        if (e >= 32 || sft == 4) break;
+        const u32 tw = __shfl_sync(FULLMASK, w, e);
+        if ((tw & 0xffu) != 0x0fu || (tw >> 24) == 255u) break;
+        if (lane == e) { kind = 2; ml = 19 + (int)(tw >> 24); off = (int)((tw >> 8) & 0xffffu); }
+        c = e + 1; sft++;
+        if (c >= 32) break;
+        w = __funnelshift_r(b0, b1, 8u * (u32)sft);
+      }
+      int cnt = c;                                             /* lanes [0, cnt) hold one sequence each */
       int incl = ml;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -536,32 +553,25 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       /* first sequence that reads its own batch's output (or is invalid: off == 0, match < 0) ends the run */
       const unsigned bad = __ballot_sync(FULLMASK, lane < cnt && (off < incl || match < 0));
       if (bad) cnt = __ffs((int)bad) - 1;
-      /* the sequence that ends the run is very often a longer literal-free match with one extra
-       * length byte (token 0x0F, offset, len): it is decoded in the same step, by the whole warp */
-      int tlen = 0, toff = 0;
-      if (cnt < 32) {
-        const u32 tw = __shfl_sync(FULLMASK, w, cnt);
-        if ((tw & 0xffu) == 0x0fu && (tw >> 24) != 255u) { tlen = 19 + (int)(tw >> 24); toff = (int)((tw >> 8) & 0xffffu); }
-      }
-      const int total = cnt ? __shfl_sync(FULLMASK, incl, cnt - 1) : 0;
-      const int top = op + total, tmatch = top - toff;
-      if (tlen && (toff == 0 || tmatch < 0 || top + tlen > oend - LZ4_MFLIMIT)) tlen = 0;   /* left to the general path */
-      if (cnt >= LZ4D_DENSE_MIN || tlen) {
+      const unsigned longm = __ballot_sync(FULLMASK, lane < cnt && kind == 2);
+      if (cnt >= LZ4D_DENSE_MIN || longm) {
+        const int total = __shfl_sync(FULLMASK, incl, cnt - 1);
+        const bool from_ring = off <= LZ4D_RING - LZ4D_DENSE_OUT - 64 && match >= ring_lo;
         {
-          /* every lane copies its own match, 4 source bytes per step: from the ring (two aligned
+          /* every lane copies its own short match, 4 source bytes per step: from the ring (two aligned
            * words + funnel shift) or, for far offsets, from the output in global memory */
-          const int mlmax = __ballot_sync(FULLMASK, ml > 16) ? 18 : (__ballot_sync(FULLMASK, ml > 8) ? 16 : 8);
-          const bool from_ring = off <= LZ4D_RING - LZ4D_DENSE_OUT - 64 && match >= ring_lo;
+          const int mls = (lane < cnt && kind == 1) ? ml : 0;
+          const int mlmax = __ballot_sync(FULLMASK, mls > 16) ? 18 : (__ballot_sync(FULLMASK, mls > 8) ? 16 : 8);
           u8* o = out + dst;
 #pragma unroll 1
           for (int k = 0; k < mlmax; k += 4) {
-            if (k < ml) {
+            if (k < mls) {
               u32 v;
               if (from_ring) {
                 const u32 m = (u32)(match + k);
                 v = __funnelshift_r(smem_ld_u32(ring, m & (LZ4D_RMASK & ~3u)), smem_ld_u32(ring, (m + 4u) & (LZ4D_RMASK & ~3u)), (m & 3u) * 8u);
               } else v = ld_u32(out + match + k);       /* may read a few bytes past the source: they are not used */
-              const int nb = ml - k;
+              const int nb = mls - k;
               const u32 r = (u32)(dst + k);
               o[k] = (u8)v; smem_st_u8(ring, r & LZ4D_RMASK, v);
               if (nb > 1) { o[k + 1] = (u8)(v >> 8); smem_st_u8(ring, (r + 1u) & LZ4D_RMASK, v >> 8); }
@@ -570,23 +580,41 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
             }
           }
         }
+        /* the long ones, by the whole warp (their sources also lie before this step's output) */
+        for (unsigned tm = longm; tm; tm &= tm - 1u) {
+          const int t = __ffs((int)tm) - 1;
+          const int td = __shfl_sync(FULLMASK, dst, t), tmt = __shfl_sync(FULLMASK, match, t), tl = __shfl_sync(FULLMASK, ml, t);
+          const bool tring = __shfl_sync(FULLMASK, (int)from_ring, t) != 0;
+          for (int k = lane; k < tl; k += 32) {
+            const u32 v = tring ? smem_ld_u8(ring, (u32)(tmt + k) & LZ4D_RMASK) : (u32)out[tmt + k];
+            out[td + k] = (u8)v;
+            smem_st_u8(ring, (u32)(td + k) & LZ4D_RMASK, v);
+          }
+        }
         __syncwarp();
-        ip += 3 * cnt; op = top;
+        ip += 3 * cnt + __popc(longm); op += total;
         LZ4D_DBGN(g_dbg_lz4d_dense_seqs, cnt);
-        if (tlen) {
-          const bool from_ring = toff <= LZ4D_RING - 512 && tmatch >= ring_lo;
+        dense_back = 0;
+        continue;
+      }
+      /* a lone long match whose source overlaps its own output (small offsets): period copy by the warp */
+      {
+        const u32 tw = __shfl_sync(FULLMASK, b0, 0);
+        const int tlen = 19 + (int)(tw >> 24), toff = (int)((tw >> 8) & 0xffffu), tmatch = op - toff;
+        if ((tw & 0xffu) == 0x0fu && (tw >> 24) != 255u && toff != 0 && tmatch >= 0 && op + tlen <= oend - LZ4_MFLIMIT) {
+          const bool tring = toff <= LZ4D_RING - 512 && tmatch >= ring_lo;
           for (int k = lane; k < tlen; k += 32) {             /* sources are all before `op`: no lane waits for another */
             const int src = tmatch + (toff >= tlen ? k : k % toff);
-            const u32 v = from_ring ? smem_ld_u8(ring, (u32)src & LZ4D_RMASK) : (u32)out[src];
+            const u32 v = tring ? smem_ld_u8(ring, (u32)src & LZ4D_RMASK) : (u32)out[src];
             out[op + k] = (u8)v;
             smem_st_u8(ring, (u32)(op + k) & LZ4D_RMASK, v);
           }
           __syncwarp();
           ip += 4; op += tlen;
           LZ4D_DBG(g_dbg_lz4d_dense_seqs);
+          dense_back = 0;
+          continue;
         }
-        dense_back = 0;
-        continue;
       }
       dense_back = dense_back < 8 ? dense_back + 1 : 8;   /* not that kind of data right here: back off */
       dense_skip = dense_back;

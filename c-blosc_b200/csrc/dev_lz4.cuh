@@ -482,7 +482,7 @@ static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d
 #endif
 #define LZ4D_RING 16384                      /* bytes of recent output mirrored in shared memory, per warp */
 #define LZ4D_RMASK (LZ4D_RING - 1)
-#define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 26) */
+#define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 27) */
 #define LZ4D_DENSE_OUT 1664                  /* a dense step writes <= 28 x 18 + 4 x 273 bytes */
 #define LZ4D_DENSE_MIN 4                     /* fewer chained 3-byte sequences than this: the 11-wide batch path is as good */
 #define LZ4D_SCRATCH 256                     /* per-warp shared scratch after the ring: sequence table + start-bit words */
@@ -630,11 +630,11 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       ldp_win12(ib, ip + lane, b0, b1, b2);
       const u32 token = b0 & 0xffu;
       const int lit = (int)(token >> 4), mln = (int)(token & 15u);
-      const int ob = 1 + lit;                                  /* window byte of the 16-bit offset (valid for lit <= 8) */
+      const int ob = 1 + lit;                                  /* window byte of the 16-bit offset (valid for lit <= 9: token, literals and offset fit the 12-byte window) */
       const u32 ow = ob < 4 ? __funnelshift_r(b0, b1, 8u * ob) : (ob < 8 ? __funnelshift_r(b1, b2, 8u * (ob - 4)) : b2 >> (8u * ((ob - 8) & 3)));
       const int off = (int)(ow & 0xffffu);
       const int L = 3 + lit, O = lit + mln + 4;
-      const bool good = lit <= 8 && mln != 15 && off >= LZ4D_BATCH_OUT;
+      const bool good = lit <= 9 && mln != 15 && off >= LZ4D_BATCH_OUT;
       int nseq = 0, consumed = 0, total = 0, my_rank = -1, my_opre = 0;
       const unsigned g3 = __ballot_sync(FULLMASK, good && lit == 0);
       if ((g3 & 0x49249249u) == 0x49249249u) {                 /* starts at lanes 0,3,...,30 */
@@ -709,7 +709,7 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       ldp_win12(ib, ip, b0, b1, b2);
       const u32 token = b0 & 0xffu;
       const int lit = (int)(token >> 4), mln = (int)(token & 15u);
-      if (lit <= 8 && mln != 15) {
+      if (lit <= 9 && mln != 15) {
         const int ml = mln + 4, total = lit + ml;
         const int ob = 1 + lit;
         const u32 ow = ob < 4 ? __funnelshift_r(b0, b1, 8u * ob) : (ob < 8 ? __funnelshift_r(b1, b2, 8u * (ob - 4)) : b2 >> (8u * (ob - 8)));

@@ -50,7 +50,7 @@ def bench_words(nbytes, np):
 def ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of one encode_kernel launch, from the committed
     `ncu --set full` summary (profiles/); None when no capture exists for this workload."""
-    name = {"lz4-shuffle-ts4-cl5-256MiB": "r1_ncu_lz4_cfg2_v16.json"}.get(workload)
+    name = {"lz4-shuffle-ts4-cl5-256MiB": "r1_ncu_lz4_cfg2_final.json"}.get(workload)
     p = os.path.join(ROOT, "profiles", name) if name else None
     if p and os.path.exists(p):
         try:
@@ -83,7 +83,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -485,7 +485,6 @@ def main():
     launches0 = pkg.launch_count()
     sampler.start()
     ms, tc, td, cb, nb = timed(dev_args, args.steps)
-    clocks = sampler.stop()
     launches = pkg.launch_count() - launches0
     prof = pkg.prof_get()
     pkg.set_profiling(False)
@@ -493,6 +492,7 @@ def main():
 
     # timed region 2: end to end from/to pinned host memory through the C ABI
     ms_h, tc_h, td_h, cb_h, nb_h = timed(host_args, args.steps)
+    clocks = sampler.stop()                  # sampled over both timed regions (each is only tens of ms long)
     assert cb_h == cb and nb_h == nbytes and torch.equal(out_h, src_h)
 
     # supplementary: 4 independent chunks in flight from 4 host threads (the _ctx API is re-entrant; the

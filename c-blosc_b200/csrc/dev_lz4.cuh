@@ -550,8 +550,9 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
         if (lane >= d) incl += t;
       }
       const int dst = op + incl - ml, match = dst - off;
-      /* first sequence that reads its own batch's output (or is invalid: off == 0, match < 0) ends the run */
-      const unsigned bad = __ballot_sync(FULLMASK, lane < cnt && (off < incl || match < 0));
+      /* first sequence that reads its own batch's output (or is invalid: off == 0, match < 0) ends the run;
+       * 8 bytes of slack because the word-wise copy below reads up to 7 bytes past the end of its source */
+      const unsigned bad = __ballot_sync(FULLMASK, lane < cnt && (off < incl + 8 || match < 0));
       if (bad) cnt = __ffs((int)bad) - 1;
       const unsigned longm = __ballot_sync(FULLMASK, lane < cnt && kind == 2);
       if (cnt >= LZ4D_DENSE_MIN || longm) {

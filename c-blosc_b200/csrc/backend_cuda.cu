@@ -36,7 +36,9 @@ static long long g_launches = 0;
 /* per-device one-time setup (opt-in to > 48 KiB dynamic shared memory) */
 extern "C" int b2_device_prepare(void) {
   CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-  CK(cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
+  CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_LZ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
+  CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_BLOSCLZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
+  CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
   return 0;
 }
@@ -197,7 +199,10 @@ extern "C" int b2_launch_decode(const DecodeArgs* a, b2_stream_t s) {
   const int ctas = (a->map.nstreams + wpc - 1) / wpc;
   if (ctas <= 0) return 0;
   ProfScope ps(B2_K_DECODE, s->s);
-  decode_kernel<<<ctas, wpc * 32, (size_t)wpc * LZ4D_SMEM, s->s>>>(*a);
+  const size_t sm = (size_t)wpc * LZ4D_SMEM;
+  if (a->codec == B2_CODEC_LZ4) decode_kernel<B2_CODEC_LZ4><<<ctas, wpc * 32, sm, s->s>>>(*a);
+  else if (a->codec == B2_CODEC_ZLIB) decode_kernel<B2_CODEC_ZLIB><<<ctas, wpc * 32, sm, s->s>>>(*a);
+  else decode_kernel<B2_CODEC_BLOSCLZ><<<ctas, wpc * 32, sm, s->s>>>(*a);
   CK(cudaGetLastError());
   return 0;
 }

@@ -16,6 +16,7 @@
 #include "b2_args.h"
 #include "dev_blosclz.cuh"
 #include "dev_common.cuh"
+#include "dev_inflate.cuh"
 #include "dev_lz4.cuh"
 
 
@@ -188,6 +189,9 @@ DEV int ld_i32(const u8* p) { return (int)ld_u32(p); }
 
 #define DECODE_WARPS 4
 /* dynamic shared memory: DECODE_WARPS * LZ4D_SMEM bytes (per-warp ring of recent output) */
+/* One instantiation per codec: the bit-serial inflate must not cost the LZ decoders registers,
+ * stack or instruction-cache footprint. */
+template <int CODEC>
 __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a) {
 #ifdef SIMT_EMU
   u8* smem = simt::g_dynsmem;
@@ -216,8 +220,10 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a)
       const u8* src = a.chunk + so;
       if (cs == len) warp_copy_bytes(out, src, len);                    /* stored raw, blosc.c:773-776 */
       else {
-        const int n = a.codec == B2_CODEC_LZ4 ? lz4_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM)
-                                               : blz_decode_warp(src, cs, out, len);
+        int n;
+        if (CODEC == B2_CODEC_LZ4) n = lz4_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM);
+        else if (CODEC == B2_CODEC_ZLIB) n = zlib_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM);
+        else n = blz_decode_warp(src, cs, out, len);
         if (n != len) err = B2_ERR_CODEC;                               /* blosc.c:778-782 */
       }
     }

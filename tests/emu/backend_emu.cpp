@@ -107,7 +107,11 @@ int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
   if (ctas <= 0) return 0;
   g_launches++;
   DecodeArgs args = *a;
-  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_SMEM, [&] { decode_kernel(args); });
+  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_SMEM, [&] {
+    if (args.codec == B2_CODEC_LZ4) decode_kernel<B2_CODEC_LZ4>(args);
+    else if (args.codec == B2_CODEC_ZLIB) decode_kernel<B2_CODEC_ZLIB>(args);
+    else decode_kernel<B2_CODEC_BLOSCLZ>(args);
+  });
   return 0;
 }
 
@@ -146,6 +150,15 @@ int emu_blz_decode(const unsigned char* src, int csize, unsigned char* dst, int 
   simt::launch(simt::Dim3(1), simt::Dim3(32), 0, [&] {
     int r = blz_decode_warp(src, csize, dst, cap);
     if ((threadIdx.x & 31) == 0) result = r;
+  });
+  return result;
+}
+
+int emu_zlib_decode(const unsigned char* src, int csize, unsigned char* dst, int cap) {
+  int result = 0;
+  simt::launch(simt::Dim3(1), simt::Dim3(32), INF_SMEM_BYTES, [&] {
+    int r = zlib_decode_warp(src, csize, dst, cap, simt::g_dynsmem);
+    if ((threadIdx.x & 31) == 17) result = r;
   });
   return result;
 }

@@ -121,6 +121,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def gpu_local_cpus(torch, index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None.  Page-locked staging buffers are
+    allocated while the process is confined to them, so that H2D / D2H DMA does not cross the
+    socket interconnect -- what any host application that cares about PCIe throughput does."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
+class near_gpu:
+    """with near_gpu(torch, index): ... -- run (and allocate) on the GPU's NUMA node."""
+
+    def __init__(self, torch, index):
+        self.cpus = gpu_local_cpus(torch, index)
+        self.saved = None
+
+    def __enter__(self):
+        if self.cpus:
+            self.saved = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *a):
+        if self.saved:
+            os.sched_setaffinity(0, self.saved)
+
+
 def load_ref():
     path = os.path.join(ROOT, "oracle", "_ref", "libblosc_ref.so")
     kind = "reference"
@@ -300,9 +338,12 @@ def run_sharded(args, np, rank, world, local_rank):
                               "decompress_gbs": total / (td / args.steps) / 1e9, "ratio": chunk / cb_chunk, "cbytes_per_chunk": cb_chunk}
 
     # end to end for the headline typesize: pinned host slice -> frame in pinned host memory -> pinned host output
-    src_h = one_h.repeat(k).pin_memory()
-    frame_h = torch.empty(bound, dtype=torch.uint8).pin_memory()
-    out_h = torch.empty(mine, dtype=torch.uint8).pin_memory()
+    numa = near_gpu(torch, dev.index)
+    with numa:
+        src_h = one_h.repeat(k).pin_memory()
+        frame_h = torch.empty(bound, dtype=torch.uint8).pin_memory()
+        out_h = torch.empty(mine, dtype=torch.uint8).pin_memory()
+    config["host_buffers"] = "page-locked, allocated on the GPU's NUMA node" if numa.cpus else "page-locked"
     timed(head_ts, src_h, frame_h, out_h, 1)
     assert torch.equal(out_h, src_h), "host round trip mismatch"
     ms_h, tc_h, td_h, fb_h = timed(head_ts, src_h, frame_h, out_h, args.steps)
@@ -427,9 +468,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    src_h = torch.from_numpy(bench_words(nbytes, np).copy()).pin_memory()
-    chunk_h = torch.zeros(nbytes + 16, dtype=torch.uint8).pin_memory()
-    out_h = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+    numa = near_gpu(torch, dev.index)
+    with numa:
+        src_h = torch.from_numpy(bench_words(nbytes, np).copy()).pin_memory()
+        chunk_h = torch.zeros(nbytes + 16, dtype=torch.uint8).pin_memory()
+        out_h = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+    config["host_buffers"] = "page-locked, allocated on the GPU's NUMA node" if numa.cpus else "page-locked"
     d_src = src_h.to(dev)
     d_chunk = torch.zeros(nbytes + 16, dtype=torch.uint8, device=dev)
     d_out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)

@@ -18,6 +18,7 @@
 #include "dev_common.cuh"
 #include "dev_inflate.cuh"
 #include "dev_lz4.cuh"
+#include "dev_zstd.cuh"
 
 
 
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a)
         int n;
         if (CODEC == B2_CODEC_LZ4) n = lz4_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM);
         else if (CODEC == B2_CODEC_ZLIB) n = zlib_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM);
+        else if (CODEC == B2_CODEC_ZSTD) n = zstd_decode_warp(src, cs, out, len, smem + (size_t)warp * LZ4D_SMEM);
         else n = blz_decode_warp(src, cs, out, len);
         if (n != len) err = B2_ERR_CODEC;                               /* blosc.c:778-782 */
       }

@@ -14,8 +14,8 @@
  *     CUDA grid is the thread pool (reference blosc.c:1706-1949);
  *   - compressors other than "blosclz" and "lz4" report -5 exactly like a reference built
  *     with -DDEACTIVATE_ZLIB/ZSTD/SNAPPY (blosc.c:573,1197-1208).  Decoding is wider: LZ4HC
- *     chunks decode (same block format) and so do zlib chunks (GPU inflate); zstd / snappy
- *     chunks report -5;
+ *     chunks decode (same block format) and so do zlib and zstd chunks (serial GPU decoders,
+ *     one lane per stream); snappy chunks report -5;
  *   - there is no CPU codec: without a CUDA device every compress/decompress call
  *     prints a message on stderr and returns -1.
  */
@@ -70,9 +70,11 @@ extern "C" {
 #define BLOSC_LZ4_FORMAT BLOSC_LZ4_LIB
 #define BLOSC_LZ4HC_FORMAT BLOSC_LZ4_LIB
 #define BLOSC_ZLIB_FORMAT BLOSC_ZLIB_LIB
+#define BLOSC_ZSTD_FORMAT BLOSC_ZSTD_LIB
 #define BLOSC_BLOSCLZ_VERSION_FORMAT 1
 #define BLOSC_LZ4_VERSION_FORMAT 1
 #define BLOSC_ZLIB_VERSION_FORMAT 1
+#define BLOSC_ZSTD_VERSION_FORMAT 1
 #define BLOSC_ALWAYS_SPLIT 1
 #define BLOSC_NEVER_SPLIT 2
 #define BLOSC_AUTO_SPLIT 3

@@ -110,6 +110,7 @@ int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
   simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_SMEM, [&] {
     if (args.codec == B2_CODEC_LZ4) decode_kernel<B2_CODEC_LZ4>(args);
     else if (args.codec == B2_CODEC_ZLIB) decode_kernel<B2_CODEC_ZLIB>(args);
+    else if (args.codec == B2_CODEC_ZSTD) decode_kernel<B2_CODEC_ZSTD>(args);
     else decode_kernel<B2_CODEC_BLOSCLZ>(args);
   });
   return 0;
@@ -159,6 +160,16 @@ int emu_zlib_decode(const unsigned char* src, int csize, unsigned char* dst, int
   simt::launch(simt::Dim3(1), simt::Dim3(32), INF_SMEM_BYTES, [&] {
     int r = zlib_decode_warp(src, csize, dst, cap, simt::g_dynsmem);
     if ((threadIdx.x & 31) == 17) result = r;
+  });
+  return result;
+}
+
+int emu_zstd_fail_line(void) { return g_zs_fail_line; }
+int emu_zstd_decode(const unsigned char* src, int csize, unsigned char* dst, int cap) {
+  int result = 0;
+  simt::launch(simt::Dim3(1), simt::Dim3(32), ZS_SMEM_BYTES, [&] {
+    int r = zstd_decode_warp(src, csize, dst, cap, simt::g_dynsmem);
+    if ((threadIdx.x & 31) == 9) result = r;
   });
   return result;
 }

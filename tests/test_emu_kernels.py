@@ -141,7 +141,7 @@ def test_library_error_codes(emu):
     assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -1
     c = chunk.copy(); c[1] = 2
     assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -9
-    c = chunk.copy(); c[2] = (c[2] & 0x1f) | (4 << 5)
+    c = chunk.copy(); c[2] = (c[2] & 0x1f) | (2 << 5)          # snappy: not built, as in the stock reference
     assert decompress(emu, "blosc_decompress_ctx", c, n)[0] == -5
     assert decompress(emu, "blosc_decompress_ctx", chunk, n - 1)[0] == -1
     c = chunk.copy(); c[20:24] = 0xff

@@ -52,15 +52,13 @@ DEV int zs_highbit(u32 v) { return 31 - __clz((int)v); }    /* v != 0 */
 
 /* n <= 32 bits at bit position `pos` of a byte string (little-endian); positions below 0 read as 0 */
 DEV u32 zs_bits_at(const u8* p, int pos, int n) {
+  int up = 0;                                                /* bits below position 0: the result is shifted up by that many */
+  if (pos < 0) { up = -pos; n += pos; pos = 0; }
   if (n <= 0) return 0;
-  if (pos < 0) {
-    if (n + pos <= 0) return 0;
-    return zs_bits_at(p, 0, n + pos) << (-pos);
-  }
   const int byte = pos >> 3, sh = pos & 7, nb = (sh + n + 7) >> 3;
   u64 v = 0;
   for (int k = 0; k < nb; k++) v |= (u64)p[byte + k] << (8 * k);
-  return (u32)((v >> sh) & ((n == 32) ? 0xffffffffull : ((1ull << n) - 1ull)));
+  return (u32)((v >> sh) & ((n == 32) ? 0xffffffffull : ((1ull << n) - 1ull))) << up;
 }
 
 /* backward bitstream over p[0, len): `pos` = number of still unread bits */

@@ -432,8 +432,15 @@ typedef struct b2_frame_job b2_frame_job;
 typedef struct {
   b2_frame_job* job;
   int index, placed;
+  int many;             /* other chunks are in flight with this one: favour streams per SM over latency */
 } b2_place;
 static void* frame_place(b2_place* pl, int32_t cbytes);
+
+static int lz4_pack_wanted(const b2_place* pl) {
+  const char* e = getenv("BLOSC_B200_LZ4_PACK");           /* 0 / 1 forces the choice (measurements) */
+  if (e && *e) return atoi(e) != 0;
+  return pl && pl->many;
+}
 
 /* header + raw payload (blosc.c:825-830) */
 static int emit_memcpyed(const uint8_t* hdr, const void* src, int src_dev, void* dest, int dest_dev, int32_t nbytes) {
@@ -543,6 +550,10 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
     ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
     /* BloscLZ at clevel >= 3: 17-bit packed table (34 KiB instead of 64 KiB) when every stream is <= 128 KiB */
     if (ea.codec == B2_CODEC_BLOSCLZ && clevel >= 3 && bs / nsplits <= 131072 && leftover <= 131072) ea.table_bytes = 32768 + 2048;
+    /* LZ4 with several chunks in flight (frames): 17-bit packed table, 8.5 KiB instead of 16 KiB per stream,
+     * when every stream is long enough for the 4096-entry table (lz4.c:710) and at most 128 KiB */
+    if (ea.codec == B2_CODEC_LZ4 && lz4_pack_wanted(pl) && leftover == 0 && bs / nsplits >= 65547 && bs / nsplits <= 131072)
+      ea.table_bytes = 8192 + 512;
     ea.queue = w->d_result + 3;
     if (b2_memset_dev(w->d_result + 2, 0, 8, w->stream)) break;          /* scan verdict scratch + work-queue counter */
     if (b2_launch_encode(&ea, w->stream)) break;
@@ -881,7 +892,7 @@ static void* frame_compress_worker(void* arg) {
     const size_t off = (size_t)i * j->chunksize;
     const size_t n = j->nbytes - off < j->chunksize ? j->nbytes - off : j->chunksize;
     int rc = -1;
-    pl.job = j; pl.index = i; pl.placed = 0;
+    pl.job = j; pl.index = i; pl.placed = 0; pl.many = j->workers > 1;
     if (!failed)
       rc = compress_impl(j->clevel, j->doshuffle, j->typesize, n, j->src + off, NULL, n + BLOSC_MAX_OVERHEAD,
                          j->compressor, j->blocksize, j->nthreads, &pl, j->dest_dev);

@@ -79,7 +79,8 @@ __global__ void encode_kernel(EncodeArgs a) {
     u8* out = a.slots + off;
     int c, need = 0;
     if (a.codec == B2_CODEC_LZ4) {
-      if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab, &need);   /* lz4.c:710,1389 */
+      if (a.table_bytes == LZ4_TAB17_BYTES) c = lz4_encode_warp<false, true>(in, len, out, len, a.accel, tab, &need);   /* host guarantees the length range */
+      else if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true>(in, len, out, len, a.accel, tab, &need);   /* lz4.c:710,1389 */
       else c = lz4_encode_warp<false>(in, len, out, len, a.accel, tab, &need);
     } else {
       c = blz_encode_warp(a.clevel, in, len, out, len, a.split_flag, tab, a.table_bytes, &need);

@@ -26,6 +26,9 @@
 #define LZ4_MFLIMIT 12
 #define LZ4_LASTLITERALS 5
 #define LZ4_TABLE_BYTES 16384          /* lz4.h:163,696  LZ4_MEMORY_USAGE 14 */
+#define LZ4_TAB17_BYTES (8192 + 512)    /* packed variant of the 4096-entry table: u16 + 1 bit per entry */
+#define LZ4_TAB17_MINLEN 65547         /* shorter streams use the 8192-entry byU16 table (lz4.c:710,1389), which cannot shrink */
+#define LZ4_TAB17_MAXLEN 131072
 
 template <bool U16>
 DEV u32 lz4_hash_at(const u8* __restrict__ s, int pos) {       /* lz4.c:777-806 */
@@ -161,17 +164,24 @@ DEV int lz4_count_tail(const StreamBase& sb, const u8* __restrict__ s, int p, in
  * aligned loads each); a sequence with < 15 literals and a short match is written by ONE
  * predicated store (lane 0 = token, lanes 1..lit = literals, the next two = offset).  The
  * 32-wide probe rounds only run when the first two probes miss. */
-template <bool U16>
+/* PACK (only with the 12-bit byU32 table, streams of at most 128 KiB): positions are 17 bits wide, so
+ * the table is kept as 4096 x u16 plus one bit per entry -- 8.5 KiB instead of 16 KiB, i.e. twice as
+ * many streams per SM.  It costs a few instructions per probe, so the host only asks for it when
+ * several chunks are in flight (frames) and throughput, not the latency of one chunk, is what counts. */
+template <bool U16, bool PACK = false>
 DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ d, const int cap,
                         const int accel, void* tabmem, int* need_out) {
   const int lane = lane_id();
   const StreamBase sb = make_stream_base(s);
   u16* tab16 = (u16*)tabmem;
   u32* tab32 = (u32*)tabmem;
-#define LZ4_TGET(h) (U16 ? (int)tab16[h] : (int)tab32[h])
-#define LZ4_TPUT(h, v) do { if (U16) tab16[h] = (u16)(v); else tab32[h] = (u32)(v); } while (0)
+  u32* tabhi = (u32*)((u8*)tabmem + 8192);                   /* PACK: bit 16 of the 4096 entries */
+#define LZ4_TGET(h) (U16 ? (int)tab16[h] : PACK ? ((int)tab16[h] | (int)(((tabhi[(h) >> 5] >> ((h) & 31u)) & 1u) << 16)) : (int)tab32[h])
+#define LZ4_TPUT(h, v) do { if (U16) tab16[h] = (u16)(v); else if (PACK) { tab16[h] = (u16)(v); const u32 m_ = 1u << ((h) & 31u); \
+                            if ((v) & 0x10000) atomicOr(&tabhi[(h) >> 5], m_); else atomicAnd(&tabhi[(h) >> 5], ~m_); } \
+                            else tab32[h] = (u32)(v); } while (0)
 
-  for (int i = lane; i < LZ4_TABLE_BYTES / 4; i += 32) tab32[i] = 0;   /* LZ4_initStream, lz4.c:1384 */
+  for (int i = lane; i < (PACK ? LZ4_TAB17_BYTES : LZ4_TABLE_BYTES) / 4; i += 32) tab32[i] = 0;   /* LZ4_initStream, lz4.c:1384 */
   __syncwarp();
 
   const bool limited = (long long)cap < (long long)n + n / 255 + 16;   /* lz4.c:1388,1395 */

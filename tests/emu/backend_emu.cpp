@@ -20,6 +20,7 @@ static int g_all_device = 0;
 static long long g_launches = 0;
 static int g_last_need = 0;
 static int g_blz_pack = 1;
+static int g_lz4_pack = 0;
 
 extern "C" {
 
@@ -27,6 +28,7 @@ void emu_set_all_device(int on) { g_all_device = on; }
 unsigned long long emu_collectives(void) { return simt::g_collectives; }
 int emu_last_need(void) { return g_last_need; }
 void emu_set_blz_pack(int on) { g_blz_pack = on; }
+void emu_set_lz4_pack(int on) { g_lz4_pack = on; }
 void emu_lz4d_counters(long long* c) { c[0] = g_dbg_lz4d_batch_seqs; c[1] = g_dbg_lz4d_fast_seqs; c[2] = g_dbg_lz4d_general_seqs; c[3] = g_dbg_lz4d_dense_seqs; }
 
 int b2_backend_init(void) { return 0; }
@@ -121,7 +123,9 @@ int emu_lz4_encode(const unsigned char* src, int n, unsigned char* dst, int cap,
   int result = 0;
   simt::launch(simt::Dim3(1), simt::Dim3(32), LZ4_TABLE_BYTES, [&] {
     int need = 0;
-    int r = n < 65536 + LZ4_MFLIMIT - 1 ? lz4_encode_warp<true>(src, n, dst, cap, accel, simt::g_dynsmem, &need)
+    int r;
+    if (g_lz4_pack && n >= LZ4_TAB17_MINLEN && n <= LZ4_TAB17_MAXLEN) r = lz4_encode_warp<false, true>(src, n, dst, cap, accel, simt::g_dynsmem, &need);
+    else r = n < 65536 + LZ4_MFLIMIT - 1 ? lz4_encode_warp<true>(src, n, dst, cap, accel, simt::g_dynsmem, &need)
                                         : lz4_encode_warp<false>(src, n, dst, cap, accel, simt::g_dynsmem, &need);
     if ((threadIdx.x & 31) == 3) g_last_need = need;
     if ((threadIdx.x & 31) == 7) result = r;

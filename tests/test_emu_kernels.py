@@ -235,3 +235,26 @@ def test_lz4_decode_unaligned_destination(emu, orc):
             dst = C.c_void_p(buf.ctypes.data + shift)
             assert emu.emu_lz4_decode(ptr(a), ci(ra), dst, ci(n)) == n
             assert (buf[shift:shift + n] == src).all() and (buf[:shift] == 0x5A).all() and (buf[shift + n:] == 0x5A).all()
+
+
+def test_lz4_packed_table_is_bit_exact(emu, orc, monkeypatch):
+    """The 17-bit packed hash table used when several chunks are in flight (frames): same bytes as
+    the plain table and the oracle, at stream level and through the library."""
+    emu.emu_set_lz4_pack(1)
+    try:
+        for kind in KINDS:
+            for n in (65547, 70001, 131072):
+                src = gen(kind, n, seed=n) if kind != "bench" else (gen("bench", 4 * n).view(np.uint32)[:n] >> 8).astype(np.uint8)
+                for accel, cap in ((5, n), (1, n), (9, n // 2), (5, n + n // 255 + 16)):
+                    a = np.zeros(cap + 64, np.uint8); b = np.zeros(cap + 64, np.uint8)
+                    ra = orc.orc_lz4_compress_fast(ptr(src), ptr(a), ci(n), ci(cap), ci(accel))
+                    rb = emu.emu_lz4_encode(ptr(src), ci(n), ptr(b), ci(cap), ci(accel))
+                    assert ra == rb and (ra <= 0 or (a[:ra] == b[:ra]).all()), (kind, n, accel, cap, ra, rb)
+    finally:
+        emu.emu_set_lz4_pack(0)
+    monkeypatch.setenv("BLOSC_B200_LZ4_PACK", "1")
+    for kind, n, ts in (("bench", 2 << 20, 4), ("mixed", 1 << 20, 2), ("text", (1 << 20) + 4096, 8)):
+        src = gen(kind, n, 3)
+        r1, c1 = compress(emu, "blosc_compress_ctx", 5, 1, ts, src, n + 16, "lz4")
+        r2, c2 = compress(orc, "orc_compress_ctx", 5, 1, ts, src, n + 16, "lz4")
+        assert r1 == r2 and (c1[:r1] == c2[:r2]).all(), (kind, n, ts)

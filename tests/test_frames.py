@@ -71,6 +71,15 @@ def test_frame_chunks_equal_oracle_chunks_emu(emu, orc, workers, monkeypatch):
     _frame_roundtrip(lib, orc, src[:4100], 4, "blosclz", 0, 4096)              # tiny last chunk (< 128: MEMCPYED)
 
 
+def test_frame_uses_packed_tables_when_chunks_overlap_emu(emu, orc, monkeypatch):
+    """With more than one chunk in flight the LZ4 encoder switches to its 17-bit packed hash table
+    (128 KiB splits): the chunks must still be the oracle's chunks."""
+    monkeypatch.setenv("BLOSC_B200_FRAME_WORKERS", "2")
+    lib = _bind(emu)
+    src = np.concatenate([bench_words(1 << 20), gen("text", 1 << 20, 2)])
+    _frame_roundtrip(lib, orc, src, 4, "lz4", 1, 1 << 20)
+
+
 def test_frame_edge_cases_emu(emu, orc):
     lib = _bind(emu)
     # empty buffer: header only

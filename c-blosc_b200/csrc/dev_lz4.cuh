@@ -166,8 +166,8 @@ DEV int lz4_count_tail(const StreamBase& sb, const u8* __restrict__ s, int p, in
  * 32-wide probe rounds only run when the first two probes miss. */
 /* PACK (only with the 12-bit byU32 table, streams of at most 128 KiB): positions are 17 bits wide, so
  * the table is kept as 4096 x u16 plus one bit per entry -- 8.5 KiB instead of 16 KiB, i.e. twice as
- * many streams per SM.  It costs a few instructions per probe, so the host only asks for it when
- * several chunks are in flight (frames) and throughput, not the latency of one chunk, is what counts. */
+ * many streams per SM.  It costs a few instructions per probe; measured with 4 chunks in flight it wins
+ * at typesize 2 and 8 and loses at typesize 4, so the host only uses it on request (BLOSC_B200_LZ4_PACK=1). */
 template <bool U16, bool PACK = false>
 DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ d, const int cap,
                         const int accel, void* tabmem, int* need_out) {

@@ -72,9 +72,10 @@ def test_frame_chunks_equal_oracle_chunks_emu(emu, orc, workers, monkeypatch):
 
 
 def test_frame_uses_packed_tables_when_chunks_overlap_emu(emu, orc, monkeypatch):
-    """With more than one chunk in flight the LZ4 encoder switches to its 17-bit packed hash table
-    (128 KiB splits): the chunks must still be the oracle's chunks."""
+    """The opt-in 17-bit packed LZ4 hash table (BLOSC_B200_LZ4_PACK=1, 128 KiB splits) with two chunks
+    in flight: the chunks must still be the oracle's chunks."""
     monkeypatch.setenv("BLOSC_B200_FRAME_WORKERS", "2")
+    monkeypatch.setenv("BLOSC_B200_LZ4_PACK", "1")
     lib = _bind(emu)
     src = np.concatenate([bench_words(1 << 20), gen("text", 1 << 20, 2)])
     _frame_roundtrip(lib, orc, src, 4, "lz4", 1, 1 << 20)

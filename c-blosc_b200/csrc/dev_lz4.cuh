@@ -12,13 +12,15 @@
  * lane wins, and only probes up to and including it are committed to the table, so
  * the table evolves exactly as in the serial code and the output is byte-identical.
  *
- * Decoder: LZ4_decompress_safe semantics (lz4.c:2022-2445).  Three tiers: a batch path
- * (every lane speculatively parses the sequence that would start at its input byte; the
- * chain of real starts is resolved with one ballot or a short shuffle walk and up to 11
- * sequences are copied 32 output bytes per instruction), a single-sequence fast path, and
- * the general path with warp-wide literal and period-replicating match copies.  A per-warp
- * shared-memory ring mirrors the last 16 KiB of output so match sources do not wait
- * behind the global stores that produced them.
+ * Decoder: LZ4_decompress_safe semantics (lz4.c:2022-2445).  Four tiers: a dense path for
+ * chains of literal-free sequences (one 3-byte sequence per lane, long matches with one
+ * extra length byte taken inline: up to 32 sequences per step, every lane copying its own
+ * match), a batch path (every lane speculatively parses the sequence that would start at
+ * its input byte; the chain of real starts is resolved with one ballot or a short shuffle
+ * walk and up to 11 sequences are copied 32 output bytes per instruction), a
+ * single-sequence fast path, and the general path with warp-wide literal and
+ * period-replicating match copies.  A per-warp shared-memory ring mirrors the last 16 KiB
+ * of output so match sources do not wait behind the global stores that produced them.
  */
 #pragma once
 #include "dev_common.cuh"
@@ -156,14 +158,14 @@ DEV int lz4_count_tail(const StreamBase& sb, const u8* __restrict__ s, int p, in
  * (LZ4_compress_fast's limitedOutput failure).  Uniform across the warp.
  * `tabmem` is LZ4_TABLE_BYTES of shared memory private to this warp.
  *
- * Hot-path shape (driven by the ncu source view of v1: ~250 dependent warp instructions
- * per sequence on the hard byte-plane): everything uniform across the warp is executed
- * redundantly by all lanes -- including the hash-table stores, so the scalar sections
- * need no broadcast and no __syncwarp.  The first two probes of every search and the
- * "test next position" probe are scalar and work on 12-byte register windows (one round of
- * aligned loads each); a sequence with < 15 literals and a short match is written by ONE
- * predicated store (lane 0 = token, lanes 1..lit = literals, the next two = offset).  The
- * 32-wide probe rounds only run when the first two probes miss. */
+ * Hot-path shape (driven by the ncu source view: ~250 dependent warp instructions per sequence
+ * on the hard byte-plane in v1, 72 now): everything uniform across the warp is computed
+ * redundantly by all lanes; table stores in the scalar sections are done by lane 0 between
+ * __syncwarp()s.  The first four probes of every search are scalar and work on 12-byte register
+ * windows (one round of aligned loads each); the "test next position" probe that follows every
+ * match is an inner loop on a lane-cached window (see below); a sequence with < 15 literals and a
+ * short match is written by ONE predicated store (lane 0 = token, lanes 1..lit = literals, the
+ * next two = offset).  The 32-wide probe rounds only run when the scalar probes miss. */
 /* PACK (only with the 12-bit byU32 table, streams of at most 128 KiB): positions are 17 bits wide, so
  * the table is kept as 4096 x u16 plus one bit per entry -- 8.5 KiB instead of 16 KiB, i.e. twice as
  * many streams per SM.  It costs a few instructions per probe; measured with 4 chunks in flight it wins

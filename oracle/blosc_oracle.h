@@ -11,6 +11,13 @@
  * against the unmodified reference compiled from /root/reference (oracle/_ref) and
  * tests/test_oracle_golden.py against the compat .cdata golden chunks.
  *
+ * Not restated here: the decode-only zlib / zstd paths.  Their
+ * algorithms live in third-party libraries vendored by the reference (zlib 1.3.1, zstd 1.5.6,
+ * internal-complibs/); the checker for those is the reference itself -- oracle/_ref is built
+ * with both -- plus the reference's golden chunks (tests/test_zlib_decode.py,
+ * tests/test_zstd_decode.py).  orc_decompress_ctx() returns -5 for such chunks, like a
+ * reference built without those codecs.
+ *
  * Every function cites the reference file:line whose behaviour it restates.
  */
 #ifndef BLOSC_ORACLE_H

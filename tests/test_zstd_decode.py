@@ -160,6 +160,13 @@ def test_compat_zstd_goldens_and_reference_chunks_emu(emu, ref):
             assert cb > 0
             r, out = decompress(emu, "blosc_decompress_ctx", chunk, n)
             assert r == n and (out[:n] == src).all() and (out[n:] == 0).all(), (kind, ts, shuf, clevel)
+    # getitem decodes only the blocks it needs (one zstd frame per block)
+    cb, chunk = compress(ref, "blosc_compress_ctx", 5, 1, 4, want, len(want) + 16, "zstd")
+    emu.blosc_getitem.restype = C.c_int
+    for start, nitems in ((0, 10), (65000, 3000), (999000, 1000), (131071, 2)):
+        item = np.full(nitems * 4 + 8, 0x33, np.uint8)
+        assert emu.blosc_getitem(ptr(chunk), ci(start), ci(nitems), ptr(item)) == nitems * 4
+        assert (item[:nitems * 4] == want[start * 4:(start + nitems) * 4]).all() and (item[nitems * 4:] == 0x33).all()
     assert emu.blosc_compress_ctx(ci(5), ci(1), sz(4), sz(1000), ptr(want), ptr(out), sz(2000), b"zstd", sz(0), ci(1)) == -5   # decode only
 
 

@@ -18,7 +18,8 @@ struct b2_stream_s {
   cudaStream_t s;
 };
 
-static int g_num_sms = 148;
+#define B2_MAX_DEVICES 64
+static int g_sms[B2_MAX_DEVICES];     /* SM count per device, filled by b2_device_prepare */
 static int g_prof_on = 0;
 static double g_prof_ms[B2_K_COUNT];
 static long long g_prof_n[B2_K_COUNT];
@@ -33,8 +34,20 @@ static long long g_launches = 0;
     }                                                                                         \
   } while (0)
 
-/* per-device one-time setup (opt-in to > 48 KiB dynamic shared memory) */
+static int num_sms(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  return (dev >= 0 && dev < B2_MAX_DEVICES && g_sms[dev] > 0) ? g_sms[dev] : 148;
+}
+
+/* per-device one-time setup (SM count; opt-in to > 48 KiB dynamic shared memory) */
 extern "C" int b2_device_prepare(void) {
+  int dev = 0, n = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < B2_MAX_DEVICES && g_sms[dev] == 0) {
+    CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    g_sms[dev] = n;
+  }
   CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_LZ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_BLOSCLZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
@@ -47,11 +60,6 @@ extern "C" int b2_device_prepare(void) {
 extern "C" int b2_backend_init(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return -1; }
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  cudaDeviceProp p;
-  CK(cudaGetDeviceProperties(&p, dev));
-  g_num_sms = p.multiProcessorCount;
   return b2_device_prepare();
 }
 
@@ -157,7 +165,7 @@ extern "C" int b2_launch_filter(const FilterArgs* a, b2_stream_t s) {
   const long long nblocks = (a->nbytes + a->blocksize - 1) / a->blocksize;
   const long long ipb = (a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1;
   long long ctas = (nblocks * ipb + FILT_WARPS - 1) / FILT_WARPS;
-  const long long cap = (long long)g_num_sms * 8;
+  const long long cap = (long long)num_sms() * 8;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   ProfScope ps(inverse ? B2_K_UNFILTER : B2_K_FILTER, s->s);
@@ -187,7 +195,7 @@ extern "C" int b2_launch_scan(const ScanArgs* a, b2_stream_t s) {
 
 extern "C" int b2_launch_compact(const CompactArgs* a, b2_stream_t s) {
   int ctas = a->nblocks;
-  if (ctas > g_num_sms * 8) ctas = g_num_sms * 8;
+  if (ctas > num_sms() * 8) ctas = num_sms() * 8;
   if (ctas <= 0) return 0;
   ProfScope ps(B2_K_COMPACT, s->s);
   compact_kernel<<<ctas, COMPACT_THREADS, 0, s->s>>>(*a);

@@ -135,11 +135,13 @@ typedef struct {
   int* h_result;        /* pinned mirror */
   uint8_t* stage[B2_STAGE_DEPTH];   /* pinned bounce slices for pageable host buffers (lazy) */
   b2_event_t stage_ev[B2_STAGE_DEPTH];
+  int stage_ok;         /* all DEPTH slices and events exist */
 } b2_ws;
 
 #define B2_MAX_WS 16
 static b2_ws g_ws[B2_MAX_WS];
 static pthread_mutex_t g_ws_mutex = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_ws_cv = PTHREAD_COND_INITIALIZER;
 static int g_backend_state = 0;   /* 0 untried, 1 ok, -1 failed */
 
 static int backend_ready(void) {
@@ -152,35 +154,72 @@ static int backend_ready(void) {
   return st > 0;
 }
 
-static b2_ws* ws_acquire(void) {
-  b2_ws* w = NULL;
-  int i, dev;
-  if (!backend_ready()) return NULL;
-  pthread_mutex_lock(&g_ws_mutex);
-  dev = b2_get_device();
-  for (i = 0; i < B2_MAX_WS; i++)          /* a workspace (stream + scratch) belongs to the device it was made on */
-    if (!g_ws[i].in_use && g_ws[i].ready && g_ws[i].dev == dev) { w = &g_ws[i]; w->in_use = 1; break; }
-  if (!w)
-    for (i = 0; i < B2_MAX_WS; i++)
-      if (!g_ws[i].in_use && !g_ws[i].ready) { w = &g_ws[i]; w->in_use = 1; break; }
-  pthread_mutex_unlock(&g_ws_mutex);
-  if (!w) { fprintf(stderr, "blosc_b200: more than %d concurrent calls\n", B2_MAX_WS); return NULL; }
-  if (!w->ready) {
-    void* p = NULL;
-    if (b2_device_prepare() || b2_stream_create(&w->stream) || b2_dev_alloc(&p, 64)) { w->in_use = 0; return NULL; }
-    w->dev = dev;
-    w->d_result = (int*)p;
-    if (b2_pinned_alloc(&p, 64)) { w->in_use = 0; return NULL; }
-    w->h_result = (int*)p;
-    w->ready = 1;
+static void buf_free(b2_buf* b) { if (b->p) b2_dev_free(b->p); b->p = NULL; b->cap = 0; }
+
+/* Everything a slot owns; the caller holds the slot (in_use) and the slot's device need not be current
+ * (device and page-locked allocations are freed by address) */
+static void ws_teardown(b2_ws* w) {
+  int k;
+  buf_free(&w->in); buf_free(&w->filt); buf_free(&w->slots); buf_free(&w->out);
+  buf_free(&w->csizes); buf_free(&w->needs); buf_free(&w->bstarts);
+  for (k = 0; k < B2_STAGE_DEPTH; k++) {
+    if (w->stage[k]) b2_pinned_free(w->stage[k]);
+    if (w->stage_ev[k]) b2_event_destroy(w->stage_ev[k]);
+    w->stage[k] = NULL; w->stage_ev[k] = NULL;
   }
-  return w;
+  w->stage_ok = 0;
+  if (w->d_result) b2_dev_free(w->d_result);
+  if (w->h_result) b2_pinned_free(w->h_result);
+  if (w->stream) b2_stream_destroy(w->stream);
+  w->d_result = NULL; w->h_result = NULL; w->stream = NULL;
+  w->ready = 0;
 }
 
 static void ws_release(b2_ws* w) {
   pthread_mutex_lock(&g_ws_mutex);
   w->in_use = 0;
+  pthread_cond_signal(&g_ws_cv);
   pthread_mutex_unlock(&g_ws_mutex);
+}
+
+/* A workspace = one stream + scratch on one device.  The reference's _ctx calls have no limit on the
+ * number of concurrent callers (each allocates its own context, blosc.c:1287-1309); here the 17th
+ * concurrent call WAITS for a slot instead of failing, and an idle slot that was made on another
+ * device is rebuilt for the caller's device when no matching or unused slot is left. */
+static b2_ws* ws_acquire(void) {
+  b2_ws* w = NULL;
+  int i, dev, rebuild = 0;
+  if (!backend_ready()) return NULL;
+  dev = b2_get_device();
+  pthread_mutex_lock(&g_ws_mutex);
+  for (;;) {
+    for (i = 0; i < B2_MAX_WS && !w; i++)
+      if (!g_ws[i].in_use && g_ws[i].ready && g_ws[i].dev == dev) w = &g_ws[i];
+    for (i = 0; i < B2_MAX_WS && !w; i++)
+      if (!g_ws[i].in_use && !g_ws[i].ready) w = &g_ws[i];
+    for (i = 0; i < B2_MAX_WS && !w; i++)
+      if (!g_ws[i].in_use) { w = &g_ws[i]; rebuild = 1; }
+    if (w) { w->in_use = 1; break; }
+    pthread_cond_wait(&g_ws_cv, &g_ws_mutex);
+  }
+  pthread_mutex_unlock(&g_ws_mutex);
+  if (rebuild) ws_teardown(w);
+  if (!w->ready) {
+    void* p = NULL;
+    int ok = 0;
+    do {
+      if (b2_device_prepare() || b2_stream_create(&w->stream)) break;
+      if (b2_dev_alloc(&p, 64)) break;
+      w->d_result = (int*)p;
+      if (b2_pinned_alloc(&p, 64)) break;
+      w->h_result = (int*)p;
+      ok = 1;
+    } while (0);
+    if (!ok) { ws_teardown(w); ws_release(w); return NULL; }
+    w->dev = dev;
+    w->ready = 1;
+  }
+  return w;
 }
 
 static int buf_ensure(b2_buf* b, size_t need) {
@@ -192,8 +231,6 @@ static int buf_ensure(b2_buf* b, size_t need) {
   b->cap = need;
   return 0;
 }
-
-static void buf_free(b2_buf* b) { if (b->p) b2_dev_free(b->p); b->p = NULL; b->cap = 0; }
 
 int blosc_free_resources(void) {                              /* blosc.h:411 */
   int i;
@@ -366,12 +403,21 @@ static int copy_any(void* dst, int dst_dev, const void* src, int src_dev, size_t
 
 static int stage_ready(b2_ws* w) {
   int k;
-  if (w->stage[0]) return 0;
+  if (w->stage_ok) return 0;
   for (k = 0; k < B2_STAGE_DEPTH; k++) {
     void* p = NULL;
-    if (b2_pinned_alloc(&p, B2_STAGE_SLICE) || b2_event_create(&w->stage_ev[k])) return -1;
-    w->stage[k] = (uint8_t*)p;
+    if (!w->stage[k]) { if (b2_pinned_alloc(&p, B2_STAGE_SLICE)) break; w->stage[k] = (uint8_t*)p; }
+    if (!w->stage_ev[k] && b2_event_create(&w->stage_ev[k])) { w->stage_ev[k] = NULL; break; }
   }
+  if (k < B2_STAGE_DEPTH) {                 /* partial: give everything back, callers fall back to a direct copy */
+    for (k = 0; k < B2_STAGE_DEPTH; k++) {
+      if (w->stage[k]) b2_pinned_free(w->stage[k]);
+      if (w->stage_ev[k]) b2_event_destroy(w->stage_ev[k]);
+      w->stage[k] = NULL; w->stage_ev[k] = NULL;
+    }
+    return -1;
+  }
+  w->stage_ok = 1;
   return 0;
 }
 
@@ -669,7 +715,10 @@ static int decode_blocks(b2_ws* w, const b2_hdr* h, int codec, const uint8_t* d_
   return w->h_result[2] < 0 ? w->h_result[2] : 0;
 }
 
-int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numinternalthreads) {
+/* max_cbytes >= 0 (frames): the chunk lives in a slot of that many bytes and must decode to exactly
+ * expect_nbytes -- a chunk header that claims more is refused before anything is copied */
+static int decompress_impl(const void* src, void* dest, size_t destsize, int numinternalthreads, long long max_cbytes,
+                           long long expect_nbytes) {
   uint8_t hb[16];
   b2_hdr h;
   int src_dev, dest_dev, codec = 0, rc, result = -1;
@@ -684,6 +733,7 @@ int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numin
     if (rc) return -1;
   } else memcpy(hb, src, 16);
   parse_header(hb, &h);
+  if (max_cbytes >= 0 && (h.cbytes < BLOSC_MAX_OVERHEAD || h.cbytes > max_cbytes || h.nbytes != expect_nbytes)) return -1;
 
   /* blosc_run_decompression_with_context, blosc.c:1463-1508 */
   if (h.nbytes == 0) return 0;
@@ -702,6 +752,9 @@ int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numin
     if (rc) return rc;
     if (h.nblocks > (h.cbytes - 16) / 4) return -1;
   }
+  /* A negative header nbytes passes every check above in the reference too; its block loop then runs
+   * zero times (nblocks <= 0, blosc.c:815, :910) and the call returns 0 without touching memory. */
+  if (h.nblocks <= 0) return 0;
   if (check_threads(numinternalthreads, h.nbytes, h.blocksize) < 0) return -1;
 
   if (h.flags & BLOSC_MEMCPYED) {                                          /* blosc.c:843-848 */
@@ -736,7 +789,11 @@ int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numin
   return result;
 }
 
-int blosc_getitem(const void* src, int start, int nitems, void* dest) {    /* blosc.c:1574-1703 */
+int blosc_decompress_ctx(const void* src, void* dest, size_t destsize, int numinternalthreads) {
+  return decompress_impl(src, dest, destsize, numinternalthreads, -1, -1);
+}
+
+static int getitem_impl(const void* src, int start, int nitems, void* dest, long long max_cbytes) {    /* blosc.c:1574-1703 */
   uint8_t hb[16];
   b2_hdr h;
   int src_dev, dest_dev, codec = 0, rc, result = -1;
@@ -753,6 +810,7 @@ int blosc_getitem(const void* src, int start, int nitems, void* dest) {    /* bl
     if (rc) return -1;
   } else memcpy(hb, src, 16);
   parse_header(hb, &h);
+  if (max_cbytes >= 0 && (h.cbytes < BLOSC_MAX_OVERHEAD || h.cbytes > max_cbytes)) return -1;
   if (h.version != BLOSC_VERSION_FORMAT) return -9;
   if (h.blocksize <= 0 || h.blocksize > h.nbytes || (size_t)h.blocksize > BLOSC_MAX_BLOCKSIZE || h.typesize <= 0)
     return -1;
@@ -800,6 +858,8 @@ int blosc_getitem(const void* src, int start, int nitems, void* dest) {    /* bl
   ws_release(w);
   return result;
 }
+
+int blosc_getitem(const void* src, int start, int nitems, void* dest) { return getitem_impl(src, start, nitems, dest, -1); }
 
 /* ------------------------------------------------------------------------- */
 /* frames: buffers larger than one chunk           */
@@ -914,7 +974,8 @@ static void* frame_decompress_worker(void* arg) {
     const size_t n = j->nbytes - off < j->chunksize ? j->nbytes - off : j->chunksize;
     int rc;
     if (failed) continue;
-    rc = blosc_decompress_ctx(j->frame + j->offsets[i], j->dest + off, n, j->nthreads);
+    rc = decompress_impl(j->frame + j->offsets[i], j->dest + off, n, j->nthreads,
+                         (long long)(j->offsets[i + 1] - j->offsets[i]), (long long)n);
     if (rc != (int)n) frame_fail(j, -1);
   }
   return NULL;
@@ -1108,7 +1169,8 @@ long long blosc_b200_frame_getitem(const void* frame, size_t framesize, size_t s
     while (done < nitems) {
       const size_t c = (start + done) / ipc, first = (start + done) % ipc;
       const size_t take = nitems - done < ipc - first ? nitems - done : ipc - first;
-      const int rc = blosc_getitem((const uint8_t*)frame + off[c], (int)first, (int)take, (uint8_t*)dest + done * ts);
+      const int rc = getitem_impl((const uint8_t*)frame + off[c], (int)first, (int)take, (uint8_t*)dest + done * ts,
+                                  (long long)(off[c + 1] - off[c]));
       if (rc != (int)(take * ts)) { result = rc < 0 ? rc : -1; break; }
       done += take;
       result += rc;

@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactArgs a)
 }
 
 
-DEV int ld_i32(const u8* p) { return (int)ld_u32(p); }
+/* byte-wise: the size prefixes may sit in the last bytes of a caller-owned device chunk, and the
+ * word-pair form of ld_u32 would touch up to 3 bytes past cbytes */
+DEV int ld_i32(const u8* p) { return (int)((u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24)); }
 
 #define DECODE_WARPS 4
 /* dynamic shared memory: DECODE_WARPS * LZ4D_SMEM bytes (per-warp ring of recent output) */

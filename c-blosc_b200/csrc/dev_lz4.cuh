@@ -39,6 +39,9 @@ DEV u32 lz4_hash_at(const u8* __restrict__ s, int pos) {       /* lz4.c:777-806 
   return (u32)(((seq << 24) * 889523592379ull) >> (64 - 12));
 }
 
+#ifndef LZ4_TILE
+#define LZ4_TILE 1                /* 0: the previous lane-cached-window chain loop (kept for A/B measurements) */
+#endif
 #define LZ4_SCALAR_PROBES 4     /* probes done one at a time before the 32-wide rounds (must be <= 64) */
 
 /* Offset from the search start of the it-th probe of the skip schedule
@@ -57,12 +60,16 @@ struct StreamBase {
   const u8* s;
   const u32* s32;
   int sal;
+  const uint4* s128;     /* the same stream seen as aligned 16-byte granules */
+  int sal16;
 };
 DEV StreamBase make_stream_base(const u8* s) {
   StreamBase b;
   b.s = s;
   b.s32 = (const u32*)((uintptr_t)s & ~(uintptr_t)3);
   b.sal = (int)((uintptr_t)s & 3u);
+  b.s128 = (const uint4*)((uintptr_t)s & ~(uintptr_t)15);
+  b.sal16 = (int)((uintptr_t)s & 15u);
   return b;
 }
 /* 12 bytes at position p as three little-endian words.  GPU: four aligned read-only word loads
@@ -107,6 +114,49 @@ DEV void ldp_win8(const StreamBase& sb, int p, u32& b0, u32& b1) {
   const u32 sh = (u32)(q & 3) * 8u;
   const u32 w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
   b0 = __funnelshift_r(w0, w1, sh); b1 = __funnelshift_r(w1, w2, sh);
+#endif
+}
+
+/* 17 bytes at position p (four words + the byte p+16) in two steps, as ldp_raw12 / ldp_take12:
+ * ldp_raw20 issues five aligned word loads (touches at most byte p+19), ldp_take17 aligns them. */
+DEV void ldp_raw20(const StreamBase& sb, int p, u32 (&r)[5]) {
+#ifdef SIMT_EMU
+  memcpy(&r[0], sb.s + p, 16); r[4] = sb.s[p + 16];
+#else
+  const u32* w = sb.s32 + ((p + sb.sal) >> 2);
+  r[0] = __ldg(w); r[1] = __ldg(w + 1); r[2] = __ldg(w + 2); r[3] = __ldg(w + 3); r[4] = __ldg(w + 4);
+#endif
+}
+DEV void ldp_take17(const StreamBase& sb, int p, const u32 (&r)[5], u32& a0, u32& a1, u32& a2, u32& a3, u32& a4b) {
+#ifdef SIMT_EMU
+  (void)sb; (void)p; a0 = r[0]; a1 = r[1]; a2 = r[2]; a3 = r[3]; a4b = r[4] & 0xffu;
+#else
+  const u32 sh = (u32)((p + sb.sal) & 3) * 8u;
+  a0 = __funnelshift_r(r[0], r[1], sh); a1 = __funnelshift_r(r[1], r[2], sh);
+  a2 = __funnelshift_r(r[2], r[3], sh); a3 = __funnelshift_r(r[3], r[4], sh);
+  a4b = (r[4] >> sh) & 0xffu;
+#endif
+}
+/* The same 17 bytes for a GATHER (every lane its own, unrelated position): two aligned 128-bit
+ * loads instead of five 32-bit ones -- a warp-wide gather costs one L1 tag cycle per distinct line
+ * and instruction, so the instruction count is what matters -- and a two-level select network that
+ * brings the five words that hold the bytes into place.  Touches [p & ~15, +32). */
+DEV void ldp_gather17(const StreamBase& sb, int p, u32& c0, u32& c1, u32& c2, u32& c3, u32& c4b) {
+#ifdef SIMT_EMU
+  memcpy(&c0, sb.s + p, 4); memcpy(&c1, sb.s + p + 4, 4); memcpy(&c2, sb.s + p + 8, 4); memcpy(&c3, sb.s + p + 12, 4);
+  c4b = sb.s[p + 16];
+#else
+  const int q = p + sb.sal16;
+  const uint4* w = sb.s128 + (q >> 4);
+  const uint4 v0 = __ldg(w), v1 = __ldg(w + 1);
+  const bool k1 = (q & 4) != 0, k2 = (q & 8) != 0;
+  const u32 sh = (u32)(q & 3) * 8u;
+  const u32 t0 = k1 ? v0.y : v0.x, t1 = k1 ? v0.z : v0.y, t2 = k1 ? v0.w : v0.z, t3 = k1 ? v1.x : v0.w;
+  const u32 t4 = k1 ? v1.y : v1.x, t5 = k1 ? v1.z : v1.y, t6 = k1 ? v1.w : v1.z;
+  const u32 u0 = k2 ? t2 : t0, u1 = k2 ? t3 : t1, u2 = k2 ? t4 : t2, u3 = k2 ? t5 : t3, u4 = k2 ? t6 : t4;
+  c0 = __funnelshift_r(u0, u1, sh); c1 = __funnelshift_r(u1, u2, sh);
+  c2 = __funnelshift_r(u2, u3, sh); c3 = __funnelshift_r(u3, u4, sh);
+  c4b = (u4 >> sh) & 0xffu;
 #endif
 }
 
@@ -200,10 +250,18 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
    * (lz4.c:1236-1294) fetches both hashes and the bytes to compare with shuffles instead of
    * reloading and re-hashing; a refill costs one round of loads per 2-3 sequences.  The 3-byte
    * sequences such a chain produces (token, offset) are parked one per lane and written together. */
+#if LZ4_TILE
+  /* Tile state for the literal-free chains (see the chained block below): lane l owns position w0+l */
+  int w0 = -(1 << 30);
+  u32 t_pack = 0, t_peers = 0, t_hash = 0;
+  int pb = -(1 << 30);                       /* base of the tile whose bytes were requested ahead of time */
+  u32 pr[5] = {0, 0, 0, 0, 0};               /* its raw aligned words */
+#else
   int w0 = -(1 << 30);
   u32 wq0 = 0, wq1 = 0, wq2 = 0, wh = 0;
   int pb = -(1 << 30);                       /* base of the window requested ahead of time */
   u32 pq0 = 0, pq1 = 0, pq2 = 0, pq3 = 0;    /* its raw aligned words */
+#endif
   int nrec = 0, recop = 0;
   u32 rec = 0;
 #define LZ4_FLUSH_CHECKED() do { if (nrec) { LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS)); } LZ4_FLUSH(); } while (0)
@@ -218,6 +276,110 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       bool have_next = false, hit = false, imm = false, have_mc = false;
       int mc_carry = 0;
 
+#if LZ4_TILE
+      bool scalar_post = post;
+      if (post && ip + 64 <= n) {
+        /* ---- chained "test next position" (lz4.c:1236-1294), speculated a tile at a time ----
+         * 99 % of the sequences of a shuffled byte-plane are found here, without literals, and the serial
+         * code is one dependent chain per sequence: hash -> table -> candidate bytes -> compare -> length
+         * -> next position.  Only the LAST link really depends on the previous sequence.  So for a tile of
+         * 32 consecutive positions every lane does the whole chain for ITS position up front, against the
+         * table as it stands when the tile is entered (phase 1: one table load, one 2 x 128-bit candidate
+         * gather, one compare -- all 32 in parallel), and the walk (phase 2) only fetches the prepared
+         * verdict of the position it lands on with a shuffle.  A verdict is stale exactly when a position
+         * inserted earlier in the same tile (sequence starts and start-2, the mask tM) has the same hash:
+         * __match_any_sync gives every lane its peers, the walk tests `peers & tM & lower lanes` and hands
+         * such a position to the scalar code below.  The table is brought up to date once per tile
+         * (highest inserted lane of every hash wins = the serial order).  The bytes of the next tile are
+         * requested one tile ahead.  Output and table are byte-identical to the serial loop. */
+        scalar_post = false;
+        bool finished = false, reanchor = false;
+        int li = 2;
+        u32 tM = 1u;                                                        /* the insert of ip-2 */
+#define LZ4_TILE_COMMIT(mask_) do { const u32 cm_ = (mask_); __syncwarp(); \
+          if (((cm_ >> lane) & 1u) && (((t_peers & cm_) >> lane) >> 1) == 0u) { LZ4_TPUT(t_hash, w0 + lane); } \
+          __syncwarp(); } while (0)
+#define LZ4_TILE_LOAD() do { \
+          u32 a0_, a1_, a2_, a3_, a4_, c0_, c1_, c2_, c3_, c4_; \
+          const int p_ = w0 + lane; \
+          if (pb == w0) ldp_take17(sb, p_, pr, a0_, a1_, a2_, a3_, a4_); \
+          else { u32 r_[5]; ldp_raw20(sb, p_, r_); ldp_take17(sb, p_, r_, a0_, a1_, a2_, a3_, a4_); } \
+          t_hash = lz4_hash_seq<U16>(a0_, a1_); \
+          __syncwarp();                                                    /* table writes of the scalar sections are visible */ \
+          const int snap_ = LZ4_TGET(t_hash); \
+          ldp_gather17(sb, snap_, c0_, c1_, c2_, c3_, c4_);                 /* snap_ < p_: every table entry predates the tile */ \
+          pb = w0 + 32; \
+          if (pb + 31 + 24 <= n) ldp_raw20(sb, pb + lane, pr); else pb = -(1 << 30);   /* not waited for */ \
+          lz4d_prefetch(s, w0 + 256, lane == 0 ? n : 0); \
+          t_peers = __match_any_sync(FULLMASK, t_hash); \
+          const u32 x1_ = a1_ ^ c1_, x2_ = a2_ ^ c2_, x3_ = a3_ ^ c3_; \
+          u32 m_;                                                          /* equal bytes after the first four: 0..12, 13 = more */ \
+          if (x1_) m_ = (u32)(__ffs((int)x1_) - 1) >> 3; \
+          else if (x2_) m_ = 4u + ((u32)(__ffs((int)x2_) - 1) >> 3); \
+          else if (x3_) m_ = 8u + ((u32)(__ffs((int)x3_) - 1) >> 3); \
+          else m_ = a4_ != c4_ ? 12u : 13u; \
+          const bool hit_ = (U16 || snap_ + 65535 >= p_) && c0_ == a0_; \
+          t_pack = (hit_ ? 1u : 0u) | (m_ << 2) | ((u32)((p_ - snap_) & 0xffff) << 8); \
+        } while (0)
+
+        if (nrec >= 24) LZ4_FLUSH_CHECKED();                                /* a tile adds at most 8 sequences */
+        w0 = ip - 2;
+        LZ4_TILE_LOAD();
+        for (;;) {
+          const u32 pk = __shfl_sync(FULLMASK, t_pack, li);
+          const u32 prs = __shfl_sync(FULLMASK, t_peers, li);
+          if (prs & tM & ((1u << li) - 1u)) {                               /* candidate was inserted inside this tile */
+            LZ4_TILE_COMMIT(tM);
+            scalar_post = true;
+            break;
+          }
+          tM |= 1u << li;                                                   /* lz4.c:1291: ip goes into the table, hit or not */
+          if (!(pk & 1u)) { LZ4_TILE_COMMIT(tM); ip++; break; }             /* lz4.c:1298; on to the search below */
+          const int off = (int)(pk >> 8);
+          int mc = (int)((pk >> 2) & 15u);
+          if (mc == 13) {
+            mc = 13 + lz4_count_tail(sb, s, ip + 17, ip - off + 17, matchlimit, n);   /* ip+64 <= n: far from matchlimit */
+            if (mc >= 15 + 255) {                                           /* very long match: general emission below */
+              LZ4_TILE_COMMIT(tM);
+              hit = true; imm = true; match = ip - off;
+              have_mc = true; mc_carry = mc;
+              break;
+            }
+          }
+          /* lz4.c:1187-1226 with 0 literals: token, offset and -- from 19 bytes on -- one length byte.
+           * Both limitedOutput checks of such a sequence ask for (op after it) + 6 <= olimit; op only
+           * grows inside a chain, so the check is made once per parked batch, before anything is
+           * written (LZ4_FLUSH_CHECKED) */
+          const bool ext = mc >= 15;
+          if (lane == nrec) { rec = (ext ? 15u | ((u32)(mc - 15) << 24) : (u32)mc) | ((u32)off << 8); recop = op; }
+          nrec++;
+          op += ext ? 4 : 3;
+          ip += mc + 4;
+          li += mc + 4;
+          anchor = ip;
+          if (ip + 64 > n) {                                                /* a match ended close to the end of the stream */
+            LZ4_TILE_COMMIT(tM);
+            if (ip >= mfl1) finished = true;                                /* lz4.c:1230-1233 */
+            else scalar_post = true;                                        /* the plain probe below takes over */
+            break;
+          }
+          if (li >= 64) { LZ4_TILE_COMMIT(tM); reanchor = true; break; }    /* jumped over the next tile */
+          if (li >= 32) {                                                   /* on to the next tile */
+            u32 carry = 0;
+            if (li - 2 < 32) tM |= 1u << (li - 2); else carry = 1u << (li - 34);   /* lz4.c:1236: start-2 goes into the table */
+            LZ4_TILE_COMMIT(tM);
+            if (nrec >= 24) LZ4_FLUSH_CHECKED();
+            w0 += 32; li -= 32; tM = carry;
+            LZ4_TILE_LOAD();
+          } else tM |= 1u << (li - 2);
+        }
+#undef LZ4_TILE_COMMIT
+#undef LZ4_TILE_LOAD
+        if (finished) break;
+        if (reanchor) continue;
+      }
+      if (scalar_post) {
+#else
       if (post && ip + 64 <= n) {
         /* ---- chained "test next position" on the lane-cached window: stays in this loop for as
          * long as every match is immediately followed by another one ---- */
@@ -287,6 +449,7 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
           continue;                                                          /* post stays true: the plain probe below takes over */
         }
       } else if (post) {
+#endif
         /* ---- fill table at ip-2, test position ip (lz4.c:1236-1294); no literals on a hit ---- */
         u32 b0, b1, b2 = 0;
         const bool wide = ip + 14 <= n;
@@ -501,7 +664,7 @@ static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d
 #define LZ4D_SMEM (LZ4D_RING + LZ4D_SCRATCH)
 
 /* LZ4_decompress_safe for one stream (lz4.c:2451-2456; safe-loop rules :2234-2436).
- * Returns the number of bytes written or -1.  offset==0 is rejected.
+ * Returns the number of bytes written or -1.  offset==0 decodes to zeros, as in the reference.
  *
  * `ring` (LZ4D_RING bytes of warp-private shared memory) mirrors the most recent output so
  * that match sources -- a few KiB back in >99% of the sequences of shuffled data -- come
@@ -638,7 +801,7 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
      * (>= LZ4D_BATCH_OUT) cannot depend on each other, so once the chain of real starts is known
      * (one ballot when every sequence is the 3-byte literal-free form, a shuffle walk otherwise)
      * all their output bytes are produced 32 per instruction. */
-    if (ip + 48 <= iend && op + LZ4D_BATCH_OUT <= oend - LZ4_MFLIMIT) {
+    if (ip + 49 <= iend && op + LZ4D_BATCH_OUT <= oend - LZ4_MFLIMIT) {   /* a 9-literal sequence of lane 31 ends at ip+41 <= iend-8 (lz4.c:2289) */
       u32 b0, b1, b2;
       ldp_win12(ib, ip + lane, b0, b1, b2);
       const u32 token = b0 & 0xffu;
@@ -785,11 +948,17 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
       } while (sb == 255);
     }
     len += 4;
-    if (match < 0 || off == 0) return -1;                     /* lz4.c:2356 */
+    if (match < 0) return -1;                                 /* lz4.c:2356 */
     cpy = op + len;
     if (cpy > oend - LZ4_LASTLITERALS) return -1;             /* lz4.c:2423 */
     __syncwarp();                                             /* earlier output must be visible to all lanes */
-    if (len <= 2048) {
+    if (off == 0) {
+      /* not a valid stream, but LZ4_decompress_safe accepts it: every copy routine first clears the
+       * destination word ("silence msan warning when offset==0", lz4.c:2386-2390; LZ4_memcpy_using_offset_base)
+       * and then replicates it, so the match decodes to zeros */
+      for (int k = lane; k < len; k += 32) out[op + k] = 0;
+      ring_lo = cpy;
+    } else if (len <= 2048) {
       /* sources lie before `op`; inside the ring they are not overwritten by this copy.  Far
        * sources are read from global memory, but the output still goes into the ring so that it
        * stays a mirror of the last 16 KiB */

@@ -425,8 +425,9 @@ last_literals:                                                  /* :1302-1329 */
 /* LZ4_decompress_safe (lz4.c:2451-2456): full-block decode, no dictionary.  The accept /
  * reject rules below are those of the "safe" decode loop (lz4.c:2234-2436); the fast
  * loop (:2077-2230) only ever handles sequences far from both buffer ends and applies
- * the same offset check, so it accepts exactly the same streams.  One deliberate
- * tightening: offset == 0 is rejected (the reference copies indeterminate bytes). */
+ * the same offset check, so it accepts exactly the same streams.  offset == 0 (invalid, but
+ * accepted) decodes to zeros in every copy routine of lz4.c 1.10 (they clear the first
+ * destination word before replicating it), and so it does here. */
 int orc_lz4_decompress_safe(const char* src, char* dst, int csize, int cap) {
   const uint8_t* in = (const uint8_t*)src;
   uint8_t* out = (uint8_t*)dst;
@@ -467,10 +468,11 @@ int orc_lz4_decompress_safe(const char* src, char* dst, int csize, int cap) {
       } while (sb == 255);
     }
     len += 4;
-    if (match < 0 || off == 0) return -1;                       /* :2356 */
+    if (match < 0) return -1;                                   /* :2356 */
     cpy = op + len;
     if (cpy > oend - LZ4_LASTLITERALS) return -1;               /* :2423 */
-    for (i = 0; i < len; i++) out[op + i] = out[match + i];
+    if (off == 0) memset(out + op, 0, (size_t)len);             /* :2386-2390: the copy routines clear the first word and replicate it */
+    else for (i = 0; i < len; i++) out[op + i] = out[match + i];
     op = cpy;
   }
   return (int)op;

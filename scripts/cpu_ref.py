@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""cpu_ref.py -- timing of the reference's own CPU implementation (oracle/_ref/libblosc_ref.so)
+at its best configuration on this host.  Used by bench.py (`--impl reference` and the
+`cpu_baseline` leg) and, stand-alone, as the sweep whose table is committed under profiles/.
+
+What is swept (VERDICT r1 "next" #1):
+  * nthreads T in {1, 8, 16, 32, 64, 128, ...} up to the host's hardware threads;
+  * both entry points: blosc_compress_ctx/blosc_decompress_ctx (which create and join a pool of
+    T threads on every call, reference blosc/blosc.c:1302-1305,1529-1532) and the global
+    blosc_compress/blosc_decompress with a persistent pool, which is how the reference's own
+    bench drives it (bench/bench.c:195,257,286);
+  * placement: no pinning; one socket (threads pinned to the CPUs of one NUMA node, buffers
+    first-touched there); all CPUs with the buffers interleaved over the NUMA nodes.
+Every cell: >= 1 s of warm-up calls, then `reps` timed round trips, MEDIAN of compress and of
+decompress separately.  value = 2*nbytes / (median tc + median td).
+
+This file is test/bench infrastructure: it executes the reference, never the product.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def bench_words(nbytes, np):
+    i = np.arange(nbytes // 4, dtype=np.uint32)
+    w = ((i << np.uint32(26)) ^ (i << np.uint32(18)) ^ (i << np.uint32(11)) ^ (i << np.uint32(3)) ^ i) & np.uint32((1 << 19) - 1)
+    return w.view(np.uint8)
+
+
+def load_ref():
+    """(kind, lib): the unmodified reference build if it travelled with the snapshot, else the oracle port."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libblosc_ref.so")
+    if os.path.exists(path):
+        return "reference", C.CDLL(path)
+    path = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], check=True)
+    return "port", C.CDLL(path)
+
+
+def numa_nodes():
+    """{node: sorted cpu list} restricted to the CPUs this process may run on."""
+    allowed = os.sched_getaffinity(0)
+    out = {}
+    base = "/sys/devices/system/node"
+    try:
+        for d in sorted(os.listdir(base)):
+            if not d.startswith("node") or not d[4:].isdigit():
+                continue
+            cpus = set()
+            for part in open(f"{base}/{d}/cpulist").read().strip().split(","):
+                if not part:
+                    continue
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= allowed
+            if cpus:
+                out[int(d[4:])] = sorted(cpus)
+    except OSError:
+        pass
+    return out or {0: sorted(allowed)}
+
+
+def physical_first(cpus):
+    """Order a CPU list so that one hardware thread of every core comes before any sibling."""
+    seen, first, rest = set(), [], []
+    for c in cpus:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        if sib in seen:
+            rest.append(c)
+        else:
+            seen.add(sib); first.append(c)
+    return first + rest
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def physical_cores():
+    seen = set()
+    for c in os.sched_getaffinity(0):
+        try:
+            seen.add(open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip())
+        except OSError:
+            seen.add(str(c))
+    return len(seen)
+
+
+_MPOL_DEFAULT, _MPOL_INTERLEAVE = 0, 3
+
+
+def set_mempolicy(interleave_nodes):
+    """set_mempolicy(2) through libc.syscall (x86-64: 238); best effort."""
+    try:
+        libc = C.CDLL(None, use_errno=True)
+        if interleave_nodes:
+            mask = 0
+            for n in interleave_nodes:
+                mask |= 1 << n
+            m = C.c_ulong(mask)
+            return libc.syscall(C.c_long(238), C.c_int(_MPOL_INTERLEAVE), C.byref(m), C.c_ulong(64)) == 0
+        return libc.syscall(C.c_long(238), C.c_int(_MPOL_DEFAULT), None, C.c_ulong(0)) == 0
+    except Exception:
+        return False
+
+
+class RefRunner:
+    """One (workload, placement) -- buffers allocated and first-touched under that placement."""
+
+    def __init__(self, np, comp_name, shuf, ts, clevel, nbytes, placement="none"):
+        self.np = np
+        self.kind, self.lib = load_ref()
+        self.pre = "blosc_" if self.kind == "reference" else "orc_"
+        self.args = (comp_name, shuf, ts, clevel, nbytes)
+        self.placement = placement
+        self.saved_aff = os.sched_getaffinity(0)
+        nodes = numa_nodes()
+        self.cpus = sorted(self.saved_aff)
+        self.note = "no pinning"
+        if placement == "socket" and len(nodes) >= 1:
+            # the node with the most CPUs available to us
+            node = max(nodes, key=lambda k: len(nodes[k]))
+            self.cpus = physical_first(nodes[node])
+            self.note = f"threads pinned to NUMA node {node} ({len(self.cpus)} cpus), buffers first-touched there"
+        elif placement == "interleave":
+            ok = set_mempolicy(list(nodes)) if len(nodes) > 1 else False
+            self.note = f"all cpus, buffers interleaved over {len(nodes)} NUMA nodes" if ok else "all cpus (interleave unavailable)"
+        if placement == "socket":
+            os.sched_setaffinity(0, set(self.cpus))
+        self.src = np.empty(nbytes, np.uint8)
+        self.src[:] = bench_words(nbytes, np)
+        self.chunk = np.zeros(nbytes + 16, np.uint8)
+        self.out = np.zeros(nbytes, np.uint8)
+        if placement == "interleave":
+            set_mempolicy(None)
+        self.pool_T = None
+
+    def close(self):
+        if self.kind == "reference" and self.pool_T is not None:
+            self.lib.blosc_destroy()
+            self.pool_T = None
+        os.sched_setaffinity(0, self.saved_aff)
+
+    def _affinity_for(self, T):
+        if self.placement == "socket":
+            os.sched_setaffinity(0, set(self.cpus[:max(1, min(T, len(self.cpus)))]))
+
+    def once(self, api, T):
+        comp_name, shuf, ts, clevel, nbytes = self.args
+        vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+        lib, pre = self.lib, self.pre
+        s, c, o = (a.ctypes.data_as(vp) for a in (self.src, self.chunk, self.out))
+        if api == "global" and self.kind == "reference":
+            if self.pool_T != T:
+                if self.pool_T is not None:
+                    lib.blosc_destroy()
+                self._affinity_for(T)                     # pool threads inherit the mask they are created under
+                lib.blosc_init()
+                lib.blosc_set_nthreads(ci(T))
+                lib.blosc_set_compressor(comp_name.encode())
+                self.pool_T = T
+            t0 = time.perf_counter()
+            cb = lib.blosc_compress(ci(clevel), ci(shuf), sz(ts), sz(nbytes), s, c, sz(nbytes + 16))
+            t1 = time.perf_counter()
+            nb = lib.blosc_decompress(c, o, sz(nbytes))
+            t2 = time.perf_counter()
+        else:
+            self._affinity_for(T)
+            f_c = getattr(lib, pre + "compress_ctx"); f_d = getattr(lib, pre + "decompress_ctx")
+            t0 = time.perf_counter()
+            cb = f_c(ci(clevel), ci(shuf), sz(ts), sz(nbytes), s, c, sz(nbytes + 16), comp_name.encode(), sz(0), ci(T))
+            t1 = time.perf_counter()
+            nb = f_d(c, o, sz(nbytes), ci(T))
+            t2 = time.perf_counter()
+        assert cb > 0 and nb == nbytes, (cb, nb)
+        return t1 - t0, t2 - t1, cb
+
+    def measure(self, api, T, reps=10, warm_s=1.0, max_s=20.0):
+        if self.kind == "port":
+            T, api = 1, "ctx"
+        t_w = time.perf_counter()
+        n = 0
+        while n < 2 or time.perf_counter() - t_w < warm_s:
+            self.once(api, T); n += 1
+        tcs, tds = [], []
+        t_m = time.perf_counter()
+        for _ in range(reps):
+            a, b, cb = self.once(api, T)
+            tcs.append(a); tds.append(b)
+            if time.perf_counter() - t_m > max_s and len(tcs) >= 3:
+                break
+        nbytes = self.args[4]
+        tc, td = statistics.median(tcs), statistics.median(tds)
+        return {"api": api, "threads": T, "placement": self.placement, "reps": len(tcs),
+                "compress_gbs": nbytes / tc / 1e9, "decompress_gbs": nbytes / td / 1e9,
+                "value": 2 * nbytes / (tc + td) / 1e9, "tc_ms": tc * 1e3, "td_ms": td * 1e3, "cbytes": cb,
+                "spread": {"tc_min_ms": min(tcs) * 1e3, "tc_max_ms": max(tcs) * 1e3, "td_min_ms": min(tds) * 1e3, "td_max_ms": max(tds) * 1e3}}
+
+
+def thread_grid(hw):
+    g = [t for t in (1, 8, 16, 32, 64, 128, 256) if t <= min(hw, 256)]
+    if hw not in g and hw <= 256:
+        g.append(hw)
+    return g
+
+
+def sweep(np, workload_args, budget_s=25.0, reps=10, full=False, log=None):
+    """Best configuration of the reference for one workload.  `full`: every cell of the grid (the
+    committed table); otherwise a bounded search: the thread grid with the persistent-pool API under
+    each placement, then the ctx API at the best cell, stopping when `budget_s` is used up."""
+    hw = len(os.sched_getaffinity(0)) or 1
+    rows = []
+    t_start = time.perf_counter()
+    kind = load_ref()[0]
+    if kind == "port":
+        r = RefRunner(np, *workload_args, placement="none")
+        rows.append(r.measure("ctx", 1, reps=3, warm_s=0.0, max_s=budget_s))
+        r.close()
+    else:
+        grid = thread_grid(hw)
+        nodes = numa_nodes()
+        placements = ["none", "socket", "interleave"] if len(nodes) > 1 else ["none"]
+        for pl in placements:
+            r = RefRunner(np, *workload_args, placement=pl)
+            try:
+                for T in grid:
+                    if pl == "socket" and T > len(r.cpus):
+                        continue
+                    if not full and T == 1:
+                        continue
+                    for api in (("global", "ctx") if full else ("global",)):
+                        left = budget_s - (time.perf_counter() - t_start)
+                        if not full and left < 1.0:
+                            break
+                        row = r.measure(api, T, reps=reps, warm_s=0.5 if not full else 1.0, max_s=2.5)
+                        row["placement_note"] = r.note
+                        rows.append(row)
+                        if log:
+                            log(row)
+            finally:
+                r.close()
+        if not full and rows:
+            b = max(rows, key=lambda x: x["value"])
+            r = RefRunner(np, *workload_args, placement=b["placement"])
+            try:
+                row = r.measure("ctx", b["threads"], reps=reps, warm_s=0.5, max_s=2.5)
+                row["placement_note"] = r.note
+                rows.append(row)
+                # the winner once more, longer: this is the number that is reported
+                row = r.measure(b["api"], b["threads"], reps=max(reps, 15), warm_s=1.0, max_s=6.0)
+                row["placement_note"] = r.note
+                row["final"] = True
+                rows.append(row)
+            finally:
+                r.close()
+    finals = [x for x in rows if x.get("final")]
+    best = max(finals or rows, key=lambda x: x["value"])
+    return {"kind": kind, "best": best, "sweep": rows, "cpu_model": cpu_model(), "hw_threads": hw,
+            "physical_cores": physical_cores(), "numa_nodes": len(numa_nodes()),
+            "seconds": time.perf_counter() - t_start}
+
+
+if __name__ == "__main__":
+    import numpy as np
+    WL = {"cfg2": ("lz4", 1, 4, 5, 256 << 20), "cfg3": ("blosclz", 2, 8, 5, 256 << 20)}
+    which = sys.argv[1:] or ["cfg2", "cfg3"]
+    res = {}
+    for w in which:
+        res[w] = sweep(np, WL[w], full=True, log=lambda r: print(w, json.dumps(r), file=sys.stderr, flush=True))
+        b = res[w]["best"]
+        print(f"{w}: best {b['value']:.1f} GB/s (c {b['compress_gbs']:.1f} / d {b['decompress_gbs']:.1f}) api={b['api']} T={b['threads']} {b['placement']}",
+              file=sys.stderr, flush=True)
+    print(json.dumps(res))

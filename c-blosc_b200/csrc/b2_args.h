@@ -32,16 +32,10 @@ typedef struct StreamMap {
   int nstreams;          /* nfull*nsplits + (leftover ? 1 : 0) */
 } StreamMap;
 
-typedef struct EncodeArgs {
-  StreamMap map;
-  const uint8_t* in;     /* filtered (or original) bytes, block-major */
-  uint8_t* slots;        /* per-stream output slots at the same offsets as `in` */
-  int* csizes;           /* [nstreams] compressed size; == stream length means "stored raw" */
-  int* needs;            /* [nstreams] smallest `maxout` with which the codec would still have succeeded */
-  int codec, clevel, accel, split_flag;
-  int table_bytes;       /* shared-memory bytes per warp */
-  int* queue;            /* zero-initialised work counter: warps pull stream numbers from it */
-} EncodeArgs;
+/* the per-workspace int32 words behind `result` / `queue` / `done` / `status` (zero between calls: the
+ * last warp of every encode / decode launch puts the counters back) */
+enum { B2_R_CBYTES = 0, B2_R_FITS = 1, B2_R_STATUS = 2, B2_R_QUEUE = 3, B2_R_DONE = 4, B2_R_STATUS_OUT = 5, B2_R_WORDS = 16 };
+#define B2_FOLD_SCAN_MAX_BLOCKS 65536   /* above this the 1024-thread scan_kernel is launched instead of the in-kernel scan */
 
 typedef struct ScanArgs {
   const int* csizes;
@@ -53,6 +47,23 @@ typedef struct ScanArgs {
   int serial;            /* 1: reproduce serial_blosc's per-split maxout clamp (blosc.c:646-651); 0: t_blosc's total-fit rule */
   long long destsize;
 } ScanArgs;
+
+typedef struct EncodeArgs {
+  StreamMap map;
+  const uint8_t* in;     /* filtered (or original) bytes, block-major */
+  uint8_t* slots;        /* per-stream output slots at the same offsets as `in` */
+  int* csizes;           /* [nstreams] compressed size; == stream length means "stored raw" */
+  int* needs;            /* [nstreams] smallest `maxout` with which the codec would still have succeeded */
+  int codec, clevel, accel, split_flag;
+  int table_bytes;       /* shared-memory bytes per warp */
+  int* queue;            /* work counter: warps pull stream numbers from it.  It only ever counts up: a launch
+                          * adds exactly nstreams + (warps launched) tickets, the backend keeps the running base */
+  unsigned queue_base;   /* first ticket of this launch (filled in by the backend) */
+  unsigned* queue_base_host;   /* HOST word behind it, owned by the workspace */
+  int* done;             /* zero-initialised count of finished streams: the warp that completes it runs the scan */
+  int fold_scan;         /* 1: that warp computes bstarts / cbytes / the fit verdict (scan) in this launch */
+  ScanArgs scan;
+} EncodeArgs;
 
 typedef struct CompactArgs {
   StreamMap map;
@@ -73,8 +84,12 @@ typedef struct DecodeArgs {
   uint8_t* out;          /* uncompressed (still filtered) bytes */
   long long out_shift;   /* subtracted from the buffer offset (getitem decodes into a small scratch) */
   int codec;
-  int* status;           /* 0 ok, else min of the negative error codes */
-  int* queue;            /* zero-initialised work counter */
+  int* status;           /* zero-initialised accumulator: 0 ok, else min of the negative error codes */
+  int* queue;            /* work counter, see EncodeArgs */
+  unsigned queue_base;
+  unsigned* queue_base_host;
+  int* done;             /* zero-initialised count of finished streams */
+  int* status_out;       /* the last warp publishes the verdict here and zeroes the three words above */
 } DecodeArgs;
 
 #ifdef __cplusplus

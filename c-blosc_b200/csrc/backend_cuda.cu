@@ -181,7 +181,10 @@ extern "C" int b2_launch_encode(const EncodeArgs* a, b2_stream_t s) {
   const int ctas = (a->map.nstreams + wpc - 1) / wpc;
   if (ctas <= 0) return 0;
   ProfScope ps(B2_K_ENCODE, s->s);
-  encode_kernel<<<ctas, wpc * 32, (size_t)wpc * a->table_bytes, s->s>>>(*a);
+  EncodeArgs args = *a;
+  args.queue_base = *a->queue_base_host;
+  *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas * (unsigned)wpc;
+  encode_kernel<<<ctas, wpc * 32, (size_t)wpc * a->table_bytes, s->s>>>(args);
   CK(cudaGetLastError());
   return 0;
 }
@@ -209,10 +212,13 @@ extern "C" int b2_launch_decode(const DecodeArgs* a, b2_stream_t s) {
   if (ctas <= 0) return 0;
   ProfScope ps(B2_K_DECODE, s->s);
   const size_t sm = (size_t)wpc * LZ4D_SMEM;
-  if (a->codec == B2_CODEC_LZ4) decode_kernel<B2_CODEC_LZ4><<<ctas, wpc * 32, sm, s->s>>>(*a);
-  else if (a->codec == B2_CODEC_ZLIB) decode_kernel<B2_CODEC_ZLIB><<<ctas, wpc * 32, sm, s->s>>>(*a);
-  else if (a->codec == B2_CODEC_ZSTD) decode_kernel<B2_CODEC_ZSTD><<<ctas, wpc * 32, sm, s->s>>>(*a);
-  else decode_kernel<B2_CODEC_BLOSCLZ><<<ctas, wpc * 32, sm, s->s>>>(*a);
+  DecodeArgs args = *a;
+  args.queue_base = *a->queue_base_host;
+  *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas * (unsigned)wpc;
+  if (a->codec == B2_CODEC_LZ4) decode_kernel<B2_CODEC_LZ4><<<ctas, wpc * 32, sm, s->s>>>(args);
+  else if (a->codec == B2_CODEC_ZLIB) decode_kernel<B2_CODEC_ZLIB><<<ctas, wpc * 32, sm, s->s>>>(args);
+  else if (a->codec == B2_CODEC_ZSTD) decode_kernel<B2_CODEC_ZSTD><<<ctas, wpc * 32, sm, s->s>>>(args);
+  else decode_kernel<B2_CODEC_BLOSCLZ><<<ctas, wpc * 32, sm, s->s>>>(args);
   CK(cudaGetLastError());
   return 0;
 }

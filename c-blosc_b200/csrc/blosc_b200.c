@@ -131,8 +131,9 @@ typedef struct {
   int in_use, ready, dev;
   b2_stream_t stream;
   b2_buf in, filt, slots, out, csizes, needs, bstarts;
-  int* d_result;        /* [0] cbytes [1] fits [2] decode status [3] work-queue counter */
+  int* d_result;        /* B2_R_* words (b2_args.h): cbytes, fits, status, work-queue and done counters */
   int* h_result;        /* pinned mirror */
+  unsigned queue_base;  /* tickets drawn from the B2_R_QUEUE counter so far (dev_chunk.cuh next_stream) */
   uint8_t* stage[B2_STAGE_DEPTH];   /* pinned bounce slices for pageable host buffers (lazy) */
   b2_event_t stage_ev[B2_STAGE_DEPTH];
   int stage_ok;         /* all DEPTH slices and events exist */
@@ -175,6 +176,14 @@ static void ws_teardown(b2_ws* w) {
   w->ready = 0;
 }
 
+/* error paths only: wait for whatever was launched and zero the counter words */
+static void ws_reset_counters(b2_ws* w) {
+  b2_stream_sync(w->stream);
+  b2_memset_dev(w->d_result, 0, 4 * B2_R_WORDS, w->stream);
+  b2_stream_sync(w->stream);
+  w->queue_base = 0;
+}
+
 static void ws_release(b2_ws* w) {
   pthread_mutex_lock(&g_ws_mutex);
   w->in_use = 0;
@@ -209,10 +218,13 @@ static b2_ws* ws_acquire(void) {
     int ok = 0;
     do {
       if (b2_device_prepare() || b2_stream_create(&w->stream)) break;
-      if (b2_dev_alloc(&p, 64)) break;
+      if (b2_dev_alloc(&p, 4 * B2_R_WORDS)) break;
       w->d_result = (int*)p;
-      if (b2_pinned_alloc(&p, 64)) break;
+      if (b2_pinned_alloc(&p, 4 * B2_R_WORDS)) break;
       w->h_result = (int*)p;
+      /* the work counters start at zero and every launch leaves them at zero again (dev_chunk.cuh) */
+      if (b2_memset_dev(w->d_result, 0, 4 * B2_R_WORDS, w->stream) || b2_stream_sync(w->stream)) break;
+      w->queue_base = 0;
       ok = 1;
     } while (0);
     if (!ok) { ws_teardown(w); ws_release(w); return NULL; }
@@ -510,7 +522,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
                          b2_place* pl, int pl_dest_dev) {
   const int compcode = blosc_compname_to_compcode(compressor);
   int32_t ts, nb, bs, nblocks, leftover, dsz;
-  int flags = 0, compformat, dont_split, src_dev, dest_dev, dofilter, fmode = 0, nsplits, result = -1;
+  int flags = 0, compformat, dont_split, src_dev, dest_dev, dofilter, fmode = 0, nsplits, result = -1, launched = 0;
   uint8_t hdr[16];
   b2_ws* w;
   const uint8_t* d_src;
@@ -603,15 +615,18 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
      * when every stream is long enough for the 4096-entry table (lz4.c:710) and at most 128 KiB */
     if (ea.codec == B2_CODEC_LZ4 && lz4_pack_wanted(pl) && leftover == 0 && bs / nsplits >= 65547 && bs / nsplits <= 131072)
       ea.table_bytes = 8192 + 512;
-    ea.queue = w->d_result + 3;
-    if (b2_memset_dev(w->d_result + 2, 0, 8, w->stream)) break;          /* scan verdict scratch + work-queue counter */
-    if (b2_launch_encode(&ea, w->stream)) break;
+    ea.queue = w->d_result + B2_R_QUEUE; ea.queue_base_host = &w->queue_base; ea.done = w->d_result + B2_R_DONE;
     sa.csizes = ea.csizes; sa.needs = ea.needs; sa.blocksize = bs; sa.leftover = leftover;
     /* do_job runs serial_blosc when nthreads == 1 or there is at most one block (blosc.c:910) */
     sa.serial = (numinternalthreads == 1 || nb / bs <= 1);
     sa.bstarts = (int*)w->bstarts.p; sa.result = w->d_result;
     sa.nsplits = nsplits; sa.nfull = nfull; sa.has_leftover = leftover > 0; sa.destsize = dsz;
-    if (b2_launch_scan(&sa, w->stream)) break;
+    /* the warp that finishes the last stream also does the block scan (no separate 1-CTA launch) */
+    ea.fold_scan = nblocks <= B2_FOLD_SCAN_MAX_BLOCKS;
+    ea.scan = sa;
+    launched = 1;
+    if (b2_launch_encode(&ea, w->stream)) break;
+    if (!ea.fold_scan && b2_launch_scan(&sa, w->stream)) break;
     if (dest_dev && !pl) d_dest = (uint8_t*)dest;
     else { if (buf_ensure(&w->out, (size_t)dsz + 64)) break; d_dest = (uint8_t*)w->out.p; }
     ca.map = ea.map; ca.in = d_codec_in; ca.slots = ea.slots; ca.csizes = ea.csizes; ca.bstarts = sa.bstarts;
@@ -638,6 +653,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
       result = 0;
     }
   } while (0);
+  if (result == -1 && launched) ws_reset_counters(w);                      /* a failed call must not leave the counters dirty */
   ws_release(w);
   if (result == -2) {
     flags |= BLOSC_MEMCPYED;
@@ -701,18 +717,21 @@ static int decode_blocks(b2_ws* w, const b2_hdr* h, int codec, const uint8_t* d_
     if (buf_ensure(&w->filt, (size_t)span + 64)) return -1;
     d_codec_out = (uint8_t*)w->filt.p;
   }
-  if (b2_memset_dev(w->d_result + 2, 0, 8, w->stream)) return -1;   /* status + work-queue counter */
   da.chunk = d_chunk; da.cbytes = h->cbytes; da.out = d_codec_out; da.out_shift = (long long)first * bs;
-  da.codec = codec; da.status = w->d_result + 2; da.queue = w->d_result + 3;
-  if (b2_launch_decode(&da, w->stream)) return -1;
+  da.codec = codec; da.status = w->d_result + B2_R_STATUS; da.queue = w->d_result + B2_R_QUEUE;
+  da.queue_base_host = &w->queue_base;
+  da.done = w->d_result + B2_R_DONE; da.status_out = w->d_result + B2_R_STATUS_OUT;
+  if (b2_launch_decode(&da, w->stream)) { ws_reset_counters(w); return -1; }
   if (doshuffle || dobitshuffle) {
     fa.src = d_codec_out; fa.dst = d_out; fa.nbytes = span; fa.blocksize = bs; fa.typesize = ts;
     fa.mode = doshuffle ? FILT_UNSHUFFLE : FILT_BITUNSHUFFLE;
-    if (b2_launch_filter(&fa, w->stream)) return -1;
+    if (b2_launch_filter(&fa, w->stream)) { ws_reset_counters(w); return -1; }
   }
-  if (b2_copy_d2h(w->h_result + 2, w->d_result + 2, 4, w->stream)) return -1;
-  if (b2_stream_sync(w->stream)) return -1;
-  return w->h_result[2] < 0 ? w->h_result[2] : 0;
+  if (b2_copy_d2h(w->h_result + B2_R_STATUS_OUT, w->d_result + B2_R_STATUS_OUT, 4, w->stream) || b2_stream_sync(w->stream)) {
+    ws_reset_counters(w);
+    return -1;
+  }
+  return w->h_result[B2_R_STATUS_OUT] < 0 ? w->h_result[B2_R_STATUS_OUT] : 0;
 }
 
 /* max_cbytes >= 0 (frames): the chunk lives in a slot of that many bytes and must decode to exactly

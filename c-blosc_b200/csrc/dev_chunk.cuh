@@ -27,10 +27,11 @@
  * numbered longest-first as far as that is knowable without looking at the data: the unsplit
  * leftover block first, then split-major (split s of every block before split s+1), so that
  * the byte-planes that turn out to be hard start in the first wave and the cheap ones fill in
- * behind them.  Returns the stream index, or -1 when the queue is empty. */
-DEV int next_stream(int* queue, const StreamMap& m) {
+ * behind them.  Returns the stream index, or -1 when the queue is empty.  Every warp of a launch
+ * draws exactly one ticket past the end, so a launch consumes nstreams + (warps launched) tickets. */
+DEV int next_stream(int* queue, unsigned base, const StreamMap& m) {
   int job = 0;
-  if (lane_id() == 0) job = atomicAdd(queue, 1);
+  if (lane_id() == 0) job = (int)((unsigned)atomicAdd(queue, 1) - base);
   job = __shfl_sync(FULLMASK, job, 0);
   if (job >= m.nstreams) return -1;
   const int nfs = m.nfull * m.nsplits;
@@ -61,6 +62,62 @@ DEV void stream_locate(const StreamMap& m, int idx, int* block, long long* off, 
 }
 
 
+/* L2 loads for words written by other SMs during this launch */
+DEV int ld_cg_i32(const int* p) {
+#ifdef SIMT_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+
+/* The block scan of t_blosc's ordered copy-out (blosc.c:1843-1856) by ONE warp: exclusive scan of the
+ * per-block compressed sizes -> bstarts, total cbytes and the "does it fit" verdict.  Run by the warp
+ * that finishes the last stream of an encode launch, so compression needs no separate scan launch
+ * (a 1-CTA launch queues behind the encoders of every other chunk in flight). */
+DEV void warp_scan_blocks(const ScanArgs& a) {
+  const int lane = lane_id();
+  const int nblocks = a.nfull + (a.has_leftover ? 1 : 0);
+  const int per = (nblocks + 31) / 32;
+  const int b0 = lane * per < nblocks ? lane * per : nblocks, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+  long long sum = 0;
+  for (int b = b0; b < b1; b++) {
+    if (b < a.nfull) for (int s = 0; s < a.nsplits; s++) sum += 4 + (long long)ld_cg_i32(&a.csizes[(long long)b * a.nsplits + s]);
+    else sum += 4 + (long long)ld_cg_i32(&a.csizes[(long long)a.nfull * a.nsplits]);
+  }
+  long long incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long t = __shfl_up_sync(FULLMASK, incl, d);
+    if (lane >= d) incl += t;
+  }
+  long long pos = 16 + 4ll * nblocks + (incl - sum);
+  int bad = 0;
+  for (int b = b0; b < b1; b++) {
+    a.bstarts[b] = (int)(pos > 0x7fffffffll ? 0x7fffffffll : pos);
+    const int ns = b < a.nfull ? a.nsplits : 1;
+    const int neblock = b < a.nfull ? a.blocksize / a.nsplits : a.leftover;
+    for (int s = 0; s < ns; s++) {
+      const long long idx = b < a.nfull ? (long long)b * a.nsplits + s : (long long)a.nfull * a.nsplits;
+      const int c = ld_cg_i32(&a.csizes[idx]);
+      if (a.serial) {
+        /* serial_blosc hands each codec call maxout = min(neblock, room left in dest) (blosc.c:646-651):
+         * a clamped call only succeeds if the stream would have fitted that smaller budget, and a
+         * raw split needs the full neblock (blosc.c:705-711) */
+        const long long room = a.destsize - (pos + 4);
+        if (room < neblock && !(room > 0 && c < neblock && ld_cg_i32(&a.needs[idx]) <= room)) bad = 1;
+      }
+      pos += 4 + (long long)c;
+    }
+  }
+  const unsigned anybad = __ballot_sync(FULLMASK, bad);
+  const long long total = 16 + 4ll * nblocks + __shfl_sync(FULLMASK, incl, 31);
+  if (lane == 0) {
+    a.result[B2_R_CBYTES] = (int)(total > 0x7fffffffll ? 0x7fffffffll : total);
+    a.result[B2_R_FITS] = (total <= a.destsize && anybad == 0u) ? 1 : 0;       /* blosc.c:1848 / :836-839 give up */
+  }
+}
+
 __global__ void encode_kernel(EncodeArgs a) {
 #ifdef SIMT_EMU
   u8* smem = simt::g_dynsmem;
@@ -69,9 +126,10 @@ __global__ void encode_kernel(EncodeArgs a) {
 #endif
   const int warp = (int)(threadIdx.x >> 5);
   void* tab = smem + (size_t)warp * a.table_bytes;
+  int mine = 0;
   for (;;) {
-    const int idx = next_stream(a.queue, a.map);
-    if (idx < 0) return;
+    const int idx = next_stream(a.queue, a.queue_base, a.map);
+    if (idx < 0) break;
     int block, len, split;
     long long off;
     stream_locate(a.map, idx, &block, &off, &len, &split);
@@ -87,8 +145,20 @@ __global__ void encode_kernel(EncodeArgs a) {
     }
     if (c <= 0 || c >= len) c = len;           /* blosc.c:705-714: incompressible split is stored raw */
     if (lane_id() == 0) { a.csizes[idx] = c; a.needs[idx] = need; }
+    mine++;
     __syncwarp();
   }
+  /* whoever completes the stream count does the block scan and puts the counters back to zero */
+  if (mine == 0) return;
+  __threadfence();
+  int last = 0;
+  if (lane_id() == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;
+  last = __shfl_sync(FULLMASK, last, 0);
+  if (!last) return;
+  __threadfence();
+  if (a.fold_scan) warp_scan_blocks(a.scan);
+  __syncwarp();
+  if (lane_id() == 0) *a.done = 0;       /* (the ticket counter is never reset: warps that got no stream may still be polling it) */
 }
 
 
@@ -138,6 +208,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
     const long long total = 16 + 4ll * nblocks + part[SCAN_THREADS - 1];
     a.result[0] = (int)(total > 0x7fffffffll ? 0x7fffffffll : total);
     a.result[1] = (total <= a.destsize && a.result[2] == 0) ? 1 : 0;   /* blosc.c:1848 / :836-839 give up */
+    a.result[2] = 0;
   }
 }
 
@@ -203,9 +274,10 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a)
   extern __shared__ __align__(16) u8 smem[];
 #endif
   const int warp = (int)(threadIdx.x >> 5);
+  int mine = 0;
   for (;;) {
-    const int idx = next_stream(a.queue, a.map);
-    if (idx < 0) return;
+    const int idx = next_stream(a.queue, a.queue_base, a.map);
+    if (idx < 0) break;
     int block, len, split;
     long long off;
     stream_locate(a.map, idx, &block, &off, &len, &split);
@@ -233,6 +305,15 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a)
       }
     }
     if (err && lane_id() == 0) atomicMin(a.status, err);
+    mine++;
     __syncwarp();
   }
+  if (mine == 0) return;
+  __threadfence();
+  int last = 0;
+  if (lane_id() == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;
+  last = __shfl_sync(FULLMASK, last, 0);
+  if (!last) return;
+  __threadfence();
+  if (lane_id() == 0) { *a.status_out = ld_cg_i32(a.status); *a.status = 0; *a.done = 0; }
 }

@@ -40,7 +40,7 @@ DEV u32 lz4_hash_at(const u8* __restrict__ s, int pos) {       /* lz4.c:777-806 
 }
 
 #ifndef LZ4_TILE
-#define LZ4_TILE 1                /* 0: the previous lane-cached-window chain loop (kept for A/B measurements) */
+#define LZ4_TILE 0                /* 1: tile-speculative chain walk (bit-exact too; measured 6 % slower on B200: 365 warp instructions per tile on one warp) */
 #endif
 #define LZ4_SCALAR_PROBES 4     /* probes done one at a time before the 32-wide rounds (must be <= 64) */
 

@@ -82,6 +82,8 @@ int b2_launch_encode(const EncodeArgs* a, b2_stream_t) {
   if (ctas <= 0) return 0;
   g_launches++;
   EncodeArgs args = *a;
+  args.queue_base = *a->queue_base_host;
+  *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas * (unsigned)wpc;
   simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * a->table_bytes, [&] { encode_kernel(args); });
   return 0;
 }
@@ -109,6 +111,8 @@ int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
   if (ctas <= 0) return 0;
   g_launches++;
   DecodeArgs args = *a;
+  args.queue_base = *a->queue_base_host;
+  *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas * (unsigned)wpc;
   simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(wpc * 32), (size_t)wpc * LZ4D_SMEM, [&] {
     if (args.codec == B2_CODEC_LZ4) decode_kernel<B2_CODEC_LZ4>(args);
     else if (args.codec == B2_CODEC_ZLIB) decode_kernel<B2_CODEC_ZLIB>(args);

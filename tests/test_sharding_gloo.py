@@ -23,7 +23,7 @@ def _data():
     return np.concatenate([bench_words(120000), gen("text", 50000, 5), gen("rand", TOTAL - 170000, 6)])
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, pipelined=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       BLOSC_B200_LIB=EMU, BLOSC_B200_FRAME_WORKERS="2")
     sys.path.insert(0, ROOT)
@@ -32,11 +32,12 @@ def _worker(rank, world, port, q):
     from cblosc_b200 import sharding
     dist.init_process_group("gloo", rank=rank, world_size=world)
     full = torch.from_numpy(_data()) if rank == 0 else None
-    frames, sizes = sharding.compress_sharded(pkg, dist, full, TOTAL, CHUNK, rank, world, "cpu", clevel=5, doshuffle=1,
-                                              typesize=TS, compressor="lz4")
+    comp = sharding.compress_sharded_pipelined if pipelined else sharding.compress_sharded
+    decomp = sharding.decompress_sharded_pipelined if pipelined else sharding.decompress_sharded
+    frames, sizes = comp(pkg, dist, full, TOTAL, CHUNK, rank, world, "cpu", clevel=5, doshuffle=1, typesize=TS, compressor="lz4")
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # bench.py's max-over-ranks reduction
-    back = sharding.decompress_sharded(pkg, dist, frames, sizes, TOTAL, CHUNK, rank, world, "cpu")
+    back = decomp(pkg, dist, frames, sizes, TOTAL, CHUNK, rank, world, "cpu")
     if rank == 0:
         q.put(([f.numpy().copy() for f in frames], sizes, back.numpy().copy(), t.item()))
     dist.barrier()
@@ -55,11 +56,15 @@ def test_shard_plan_covers_everything(pkg):
     assert sharding.byte_ranges(10, 4, 8)[3:] == [(10, 10)] * 5     # more ranks than chunks: empty tails
 
 
-def test_two_rank_gloo_sharded_roundtrip(emu, orc):
+import pytest
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_two_rank_gloo_sharded_roundtrip(emu, orc, pipelined):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, pipelined)) for r in range(2)]
     for p in procs:
         p.start()
     frames, sizes, back, tmax = q.get(timeout=300)

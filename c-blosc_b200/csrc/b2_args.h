@@ -56,6 +56,7 @@ typedef struct EncodeArgs {
   int* needs;            /* [nstreams] smallest `maxout` with which the codec would still have succeeded */
   int codec, clevel, accel, split_flag;
   int table_bytes;       /* shared-memory bytes per warp */
+  int num_sms;           /* filled in by the backend (team kernel: spreads the walker warps over the SM sub-partitions) */
   int* queue;            /* work counter: warps pull stream numbers from it.  It only ever counts up: a launch
                           * adds exactly nstreams + (warps launched) tickets, the backend keeps the running base */
   unsigned queue_base;   /* first ticket of this launch (filled in by the backend) */

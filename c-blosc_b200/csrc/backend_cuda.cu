@@ -9,6 +9,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "b2_backend.h"
 #include "dev_chunk.cuh"
@@ -49,6 +50,7 @@ extern "C" int b2_device_prepare(void) {
     g_sms[dev] = n;
   }
   CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  CK(cudaFuncSetAttribute(encode_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TEAM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_LZ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_BLOSCLZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
@@ -174,7 +176,28 @@ extern "C" int b2_launch_filter(const FilterArgs* a, b2_stream_t s) {
   return 0;
 }
 
+/* LZ4 with the plain 16 KiB table runs in team mode (BLOSC_B200_LZ4_TEAM=0 falls back to one warp per stream) */
+static int team_wanted(const EncodeArgs* a) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("BLOSC_B200_LZ4_TEAM"); env = (e && *e) ? atoi(e) != 0 : 1; }
+  return env && a->codec == B2_CODEC_LZ4 && a->table_bytes == LZ4_TABLE_BYTES;
+}
+
 extern "C" int b2_launch_encode(const EncodeArgs* a, b2_stream_t s) {
+  if (team_wanted(a)) {
+    int ctas = a->map.nstreams;
+    const int cap = num_sms() * TEAM_CTAS_PER_SM;
+    if (ctas > cap) ctas = cap;
+    if (ctas <= 0) return 0;
+    ProfScope ps(B2_K_ENCODE, s->s);
+    EncodeArgs args = *a;
+    args.num_sms = num_sms();
+    args.queue_base = *a->queue_base_host;
+    *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas;      /* one ticket-drawing warp per CTA */
+    encode_team_kernel<<<ctas, TEAM_WARPS * 32, TEAM_SMEM_BYTES, s->s>>>(args);
+    CK(cudaGetLastError());
+    return 0;
+  }
   int wpc = 65536 / a->table_bytes;           /* 64 KiB of tables per CTA -> 3 CTAs per SM */
   if (wpc > 4) wpc = 4;
   if (wpc < 1) wpc = 1;

@@ -162,6 +162,62 @@ __global__ void encode_kernel(EncodeArgs a) {
 }
 
 
+/* LZ4 in team mode (dev_lz4.cuh): one CTA of four warps per stream -- a walker that owns the parse,
+ * the table and the output, and three preparers that work ahead of it.  Shared memory: the stream's
+ * hash table, then the Lz4Team block.  The walker warp alone draws tickets, counts finished streams
+ * and runs the block scan, exactly as a warp of encode_kernel does. */
+#define TEAM_WARPS 4
+#define TEAM_CTAS_PER_SM 8
+#define TEAM_SMEM_BYTES (LZ4_TABLE_BYTES + ((LZ4T_SMEM_BYTES + 15) & ~15))
+__global__ void __launch_bounds__(TEAM_WARPS * 32, TEAM_CTAS_PER_SM) encode_team_kernel(EncodeArgs a) {
+#ifdef SIMT_EMU
+  u8* smem = simt::g_dynsmem;
+#else
+  extern __shared__ __align__(16) u8 smem[];
+#endif
+  void* tab = smem;
+  Lz4Team* tm = (Lz4Team*)(smem + LZ4_TABLE_BYTES);
+  const int warp = (int)(threadIdx.x >> 5);
+  /* CTAs land on the SMs round-robin, so the CTAs of one SM differ in blockIdx / num_sms: rotating the
+   * walker role with it puts the (busy) walkers of co-resident teams on different sub-partitions */
+  const int walker = (int)((blockIdx.x / (unsigned)(a.num_sms > 0 ? a.num_sms : 1)) & 3u);
+  if (threadIdx.x == 0) { tm->cmd = 0; tm->gen = 0; }
+  __syncthreads();
+  if (warp != walker) { lz4_team_preparer(tm, tab, (warp - walker - 1) & 3); return; }
+  int mine = 0;
+  for (;;) {
+    const int idx = next_stream(a.queue, a.queue_base, a.map);
+    if (idx < 0) break;
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    const u8* in = a.in + off;
+    u8* out = a.slots + off;
+    int c, need = 0;
+    if (len < 65536 + LZ4_MFLIMIT - 1) c = lz4_encode_warp<true, false, true>(in, len, out, len, a.accel, tab, &need, tm);   /* lz4.c:710,1389 */
+    else c = lz4_encode_warp<false, false, true>(in, len, out, len, a.accel, tab, &need, tm);
+    if (c <= 0 || c >= len) c = len;           /* blosc.c:705-714: incompressible split is stored raw */
+    if (lane_id() == 0) { a.csizes[idx] = c; a.needs[idx] = need; }
+    mine++;
+    __syncwarp();
+  }
+  if (lane_id() == 0) *(volatile int*)&tm->cmd = LZ4T_QUIT;
+  __syncwarp();
+  __threadfence_block();
+  bar_arrive(LZ4T_BAR_GO(0), 64); bar_arrive(LZ4T_BAR_GO(1), 64); bar_arrive(LZ4T_BAR_GO(2), 64);
+  if (mine == 0) return;
+  __threadfence();
+  int last = 0;
+  if (lane_id() == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;
+  last = __shfl_sync(FULLMASK, last, 0);
+  if (!last) return;
+  __threadfence();
+  if (a.fold_scan) warp_scan_blocks(a.scan);
+  __syncwarp();
+  if (lane_id() == 0) *a.done = 0;
+}
+
+
 #define SCAN_THREADS 1024
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
   __shared__ long long part[SCAN_THREADS];

@@ -31,6 +31,23 @@ typedef unsigned long long u64;
 
 DEV int lane_id() { return (int)(threadIdx.x & 31u); }
 
+/* Named CTA barriers for warp-specialised producer / consumer hand-offs: `nthreads` threads in total
+ * take part (arrivers + waiters); bar_arrive does not block.  Barrier 0 is __syncthreads. */
+DEV void bar_sync(int id, int nthreads) {
+#ifdef SIMT_EMU
+  simt::named_barrier(id, nthreads, true);
+#else
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+#endif
+}
+DEV void bar_arrive(int id, int nthreads) {
+#ifdef SIMT_EMU
+  simt::named_barrier(id, nthreads, false);
+#else
+  asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 /* Unaligned little-endian 32-bit load. On the GPU: two aligned word loads + funnel
  * shift (global/shared loads must be naturally aligned). */
 DEV u32 ld_u32(const u8* p) {
@@ -71,6 +88,15 @@ DEV u32 smem_ld_u32(smem_addr_t base, u32 off) {                 /* off % 4 == 0
   return v;
 }
 #endif
+
+/* 8 bytes of shared memory at a 32-bit shared-window address (off % 8 == 0) */
+DEV void smem_ld_u32x2(smem_addr_t base, u32 off, u32& x, u32& y) {
+#ifdef SIMT_EMU
+  memcpy(&x, base + off, 4); memcpy(&y, base + off + 4, 4);
+#else
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(base + off));
+#endif
+}
 
 DEV void st_u32_bytes(u8* p, u32 v) {   /* unaligned 32-bit store, byte by byte */
   p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24);

@@ -39,9 +39,6 @@ DEV u32 lz4_hash_at(const u8* __restrict__ s, int pos) {       /* lz4.c:777-806 
   return (u32)(((seq << 24) * 889523592379ull) >> (64 - 12));
 }
 
-#ifndef LZ4_TILE
-#define LZ4_TILE 0                /* 1: tile-speculative chain walk (bit-exact too; measured 6 % slower on B200: 365 warp instructions per tile on one warp) */
-#endif
 #define LZ4_SCALAR_PROBES 4     /* probes done one at a time before the 32-wide rounds (must be <= 64) */
 
 /* Offset from the search start of the it-th probe of the skip schedule
@@ -204,6 +201,94 @@ DEV int lz4_count_tail(const StreamBase& sb, const u8* __restrict__ s, int p, in
   return warp_count_match(s, p, q, limit);
 }
 
+/* ---- team mode: one CTA of four warps per stream ------------------------------------------------
+ * A lone warp spends ~6 cycles per instruction on its dependent chain (ALU latency 4, one issue
+ * per 2 cycles and pipe), so on a hard byte-plane the serial LZ4 loop is bound by the NUMBER of
+ * instructions one warp has to issue per sequence, not by memory.  In team mode the stream's warp
+ * ("walker") keeps only what is inherently serial -- which position the parse lands on next, the
+ * table stores, the output -- and three helper warps ("preparers") do the rest ahead of it:
+ * for every position of a 32-position tile a preparer computes hash, table lookup, candidate
+ * gather, 17-byte compare and packs the verdict {hit, match length, offset} into a shared-memory
+ * ring; the walker reads the verdict of the position it lands on with one 8-byte shared load.
+ * A verdict can be stale: the preparer of tile t starts when the walker has finished tile t-3, so
+ * it cannot have seen the table stores of tiles t-2 .. t.  The walker keeps the hashes of exactly
+ * those stores in a 32-entry register ring (one per lane) and tests "is the hash of this position
+ * among them" with one compare + ballot; such a position (rare) is resolved by the scalar code.
+ * The parse, the table and the output stay byte-identical to LZ4_compress_fast.
+ * Hand-offs use named barriers (bar.sync / bar.arrive, 64 threads each): GO(i) walker -> preparer i
+ * "tile may be prepared", FULL(i) preparer i -> walker "tile is in the ring"; preparer i owns the
+ * tiles i, i+3, i+6, ... of a session.  Waiting warps are descheduled by the barrier hardware. */
+#ifdef SIMT_EMU
+static long long g_dbg_lz4t_sessions = 0, g_dbg_lz4t_seqs = 0, g_dbg_lz4t_stale = 0, g_dbg_lz4t_x[6];
+#define LZ4T_DBG(x) do { if (lane_id() == 0) (x)++; } while (0)
+#else
+#define LZ4T_DBG(x) do {} while (0)
+#endif
+#define LZ4T_RING 256                      /* positions in the verdict ring = 8 tiles */
+#define LZ4T_BAR_FULL(i) (1 + (i))
+#define LZ4T_BAR_GO(i) (4 + (i))
+#define LZ4T_QUIT 1
+#define LZ4T_END 0xffffffffu               /* verdict of a tile too close to the end of the stream to be prepared */
+#define LZ4T_LONG 13                       /* match-length field: 13 = "13 or more bytes after the first four" */
+struct Lz4Team {
+  uint2 vd[LZ4T_RING];                     /* .x verdict: bit 0 hit, bits 2..5 length field, bits 8..23 offset; .y hash */
+  const u8* s;                             /* current stream */
+  int n;
+  int base;                                /* position of ring entry 0 in this session */
+  int gen;                                 /* session number: a preparer restarts at its first tile when it changes */
+  int cmd;                                 /* LZ4T_QUIT ends the preparers */
+  int u16;                                 /* table flavour of the current stream */
+};
+#define LZ4T_SMEM_BYTES ((int)sizeof(Lz4Team))
+
+DEV int lz4t_ld_i32(const int* p) { return *(const volatile int*)p; }
+
+template <bool U16>
+DEV void lz4_team_prepare_tile(Lz4Team* tm, const void* tabmem, const u8* s, int n, int w0) {
+  const int lane = lane_id();
+  const int p = w0 + lane;
+  const int e = (w0 - lz4t_ld_i32(&tm->base) + lane) & (LZ4T_RING - 1);
+  if (w0 + 31 + 24 > n) { tm->vd[e] = make_uint2(LZ4T_END, 0u); return; }     /* loads below reach byte p+19 (+3) */
+  const StreamBase sb = make_stream_base(s);
+  u32 r[5], a0, a1, a2, a3, a4, c0, c1, c2, c3, c4;
+  ldp_raw20(sb, p, r);
+  ldp_take17(sb, p, r, a0, a1, a2, a3, a4);
+  const u32 h = lz4_hash_seq<U16>(a0, a1);
+  /* racing with the walker's stores is fine: whatever this read misses is in the walker's ring */
+  const int snap = U16 ? (int)((const volatile u16*)tabmem)[h] : (int)((const volatile u32*)tabmem)[h];
+  u32 vx = 0;
+  if (snap < p) {                                      /* always true for entries the serial code could see here */
+    ldp_gather17(sb, snap, c0, c1, c2, c3, c4);
+    const u32 x1 = a1 ^ c1, x2 = a2 ^ c2, x3 = a3 ^ c3;
+    u32 m;
+    if (x1) m = (u32)(__ffs((int)x1) - 1) >> 3;
+    else if (x2) m = 4u + ((u32)(__ffs((int)x2) - 1) >> 3);
+    else if (x3) m = 8u + ((u32)(__ffs((int)x3) - 1) >> 3);
+    else m = a4 != c4 ? 12u : (u32)LZ4T_LONG;
+    const bool hit = (U16 || snap + 65535 >= p) && c0 == a0;
+    vx = (hit ? 1u : 0u) | (m << 2) | ((u32)((p - snap) & 0xffff) << 8);
+  }
+  tm->vd[e] = make_uint2(vx, h);
+}
+
+/* body of preparer warp i (0..2); returns when the walker posts LZ4T_QUIT */
+DEV void lz4_team_preparer(Lz4Team* tm, const void* tabmem, int i) {
+  int gen_seen = -1, tile = i;
+  for (;;) {
+    bar_sync(LZ4T_BAR_GO(i), 64);
+    if (lz4t_ld_i32(&tm->cmd) == LZ4T_QUIT) return;
+    const int gen = lz4t_ld_i32(&tm->gen);
+    if (gen != gen_seen) { gen_seen = gen; tile = i; }
+    const u8* s = *(const u8* const volatile*)&tm->s;
+    const int n = lz4t_ld_i32(&tm->n), w0 = lz4t_ld_i32(&tm->base) + 32 * tile;
+    if (lz4t_ld_i32(&tm->u16)) lz4_team_prepare_tile<true>(tm, tabmem, s, n, w0);
+    else lz4_team_prepare_tile<false>(tm, tabmem, s, n, w0);
+    tile += 3;
+    __threadfence_block();
+    bar_arrive(LZ4T_BAR_FULL(i), 64);
+  }
+}
+
 /* Returns the compressed size, or 0 when the stream does not fit in `cap`
  * (LZ4_compress_fast's limitedOutput failure).  Uniform across the warp.
  * `tabmem` is LZ4_TABLE_BYTES of shared memory private to this warp.
@@ -220,9 +305,9 @@ DEV int lz4_count_tail(const StreamBase& sb, const u8* __restrict__ s, int p, in
  * the table is kept as 4096 x u16 plus one bit per entry -- 8.5 KiB instead of 16 KiB, i.e. twice as
  * many streams per SM.  It costs a few instructions per probe; measured with 4 chunks in flight it wins
  * at typesize 2 and 8 and loses at typesize 4, so the host only uses it on request (BLOSC_B200_LZ4_PACK=1). */
-template <bool U16, bool PACK = false>
+template <bool U16, bool PACK = false, bool TEAM = false>
 DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ d, const int cap,
-                        const int accel, void* tabmem, int* need_out) {
+                        const int accel, void* tabmem, int* need_out, Lz4Team* tm = nullptr) {
   const int lane = lane_id();
   const StreamBase sb = make_stream_base(s);
   u16* tab16 = (u16*)tabmem;
@@ -250,18 +335,10 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
    * (lz4.c:1236-1294) fetches both hashes and the bytes to compare with shuffles instead of
    * reloading and re-hashing; a refill costs one round of loads per 2-3 sequences.  The 3-byte
    * sequences such a chain produces (token, offset) are parked one per lane and written together. */
-#if LZ4_TILE
-  /* Tile state for the literal-free chains (see the chained block below): lane l owns position w0+l */
-  int w0 = -(1 << 30);
-  u32 t_pack = 0, t_peers = 0, t_hash = 0;
-  int pb = -(1 << 30);                       /* base of the tile whose bytes were requested ahead of time */
-  u32 pr[5] = {0, 0, 0, 0, 0};               /* its raw aligned words */
-#else
   int w0 = -(1 << 30);
   u32 wq0 = 0, wq1 = 0, wq2 = 0, wh = 0;
   int pb = -(1 << 30);                       /* base of the window requested ahead of time */
   u32 pq0 = 0, pq1 = 0, pq2 = 0, pq3 = 0;    /* its raw aligned words */
-#endif
   int nrec = 0, recop = 0;
   u32 rec = 0;
 #define LZ4_FLUSH_CHECKED() do { if (nrec) { LZ4_LIMIT(op + (1 + LZ4_LASTLITERALS)); } LZ4_FLUSH(); } while (0)
@@ -276,73 +353,54 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
       bool have_next = false, hit = false, imm = false, have_mc = false;
       int mc_carry = 0;
 
-#if LZ4_TILE
       bool scalar_post = post;
-      if (post && ip + 64 <= n) {
-        /* ---- chained "test next position" (lz4.c:1236-1294), speculated a tile at a time ----
-         * 99 % of the sequences of a shuffled byte-plane are found here, without literals, and the serial
-         * code is one dependent chain per sequence: hash -> table -> candidate bytes -> compare -> length
-         * -> next position.  Only the LAST link really depends on the previous sequence.  So for a tile of
-         * 32 consecutive positions every lane does the whole chain for ITS position up front, against the
-         * table as it stands when the tile is entered (phase 1: one table load, one 2 x 128-bit candidate
-         * gather, one compare -- all 32 in parallel), and the walk (phase 2) only fetches the prepared
-         * verdict of the position it lands on with a shuffle.  A verdict is stale exactly when a position
-         * inserted earlier in the same tile (sequence starts and start-2, the mask tM) has the same hash:
-         * __match_any_sync gives every lane its peers, the walk tests `peers & tM & lower lanes` and hands
-         * such a position to the scalar code below.  The table is brought up to date once per tile
-         * (highest inserted lane of every hash wins = the serial order).  The bytes of the next tile are
-         * requested one tile ahead.  Output and table are byte-identical to the serial loop. */
+      if (TEAM && post && ip + 64 <= n) {
+        /* ---- chained "test next position" (lz4.c:1236-1294) with the verdicts prepared by the helper
+         * warps (see "team mode" above) ---- */
         scalar_post = false;
         bool finished = false, reanchor = false;
-        int li = 2;
-        u32 tM = 1u;                                                        /* the insert of ip-2 */
-#define LZ4_TILE_COMMIT(mask_) do { const u32 cm_ = (mask_); __syncwarp(); \
-          if (((cm_ >> lane) & 1u) && (((t_peers & cm_) >> lane) >> 1) == 0u) { LZ4_TPUT(t_hash, w0 + lane); } \
-          __syncwarp(); } while (0)
-#define LZ4_TILE_LOAD() do { \
-          u32 a0_, a1_, a2_, a3_, a4_, c0_, c1_, c2_, c3_, c4_; \
-          const int p_ = w0 + lane; \
-          if (pb == w0) ldp_take17(sb, p_, pr, a0_, a1_, a2_, a3_, a4_); \
-          else { u32 r_[5]; ldp_raw20(sb, p_, r_); ldp_take17(sb, p_, r_, a0_, a1_, a2_, a3_, a4_); } \
-          t_hash = lz4_hash_seq<U16>(a0_, a1_); \
-          __syncwarp();                                                    /* table writes of the scalar sections are visible */ \
-          const int snap_ = LZ4_TGET(t_hash); \
-          ldp_gather17(sb, snap_, c0_, c1_, c2_, c3_, c4_);                 /* snap_ < p_: every table entry predates the tile */ \
-          pb = w0 + 32; \
-          if (pb + 31 + 24 <= n) ldp_raw20(sb, pb + lane, pr); else pb = -(1 << 30);   /* not waited for */ \
-          lz4d_prefetch(s, w0 + 256, lane == 0 ? n : 0); \
-          t_peers = __match_any_sync(FULLMASK, t_hash); \
-          const u32 x1_ = a1_ ^ c1_, x2_ = a2_ ^ c2_, x3_ = a3_ ^ c3_; \
-          u32 m_;                                                          /* equal bytes after the first four: 0..12, 13 = more */ \
-          if (x1_) m_ = (u32)(__ffs((int)x1_) - 1) >> 3; \
-          else if (x2_) m_ = 4u + ((u32)(__ffs((int)x2_) - 1) >> 3); \
-          else if (x3_) m_ = 8u + ((u32)(__ffs((int)x3_) - 1) >> 3); \
-          else m_ = a4_ != c4_ ? 12u : 13u; \
-          const bool hit_ = (U16 || snap_ + 65535 >= p_) && c0_ == a0_; \
-          t_pack = (hit_ ? 1u : 0u) | (m_ << 2) | ((u32)((p_ - snap_) & 0xffff) << 8); \
-        } while (0)
-
-        if (nrec >= 24) LZ4_FLUSH_CHECKED();                                /* a tile adds at most 8 sequences */
-        w0 = ip - 2;
-        LZ4_TILE_LOAD();
+        if (nrec >= 24) LZ4_FLUSH_CHECKED();
+        LZ4T_DBG(g_dbg_lz4t_sessions);
+        const int base = ip - 2;
+        if (lane == 0) {
+          tm->s = s; tm->n = n; tm->u16 = U16 ? 1 : 0; tm->base = base;
+          tm->gen = lz4t_ld_i32(&tm->gen) + 1;
+        }
+        __syncwarp();
+        __threadfence_block();
+        bar_arrive(LZ4T_BAR_GO(0), 64); bar_arrive(LZ4T_BAR_GO(1), 64); bar_arrive(LZ4T_BAR_GO(2), 64);
+        u32 out = 7u;                         /* preparers that were told to go and whose tile has not been taken yet */
+        int t = 0, li = 2;                    /* current tile of the session and position inside it: ip == base + 32 t + li */
+        u32 ring_h = 0xffffffffu;             /* lane l: hash of the (l mod 32)-th most recent table store, or invalid */
+        int ring_n = 0, rs_lo = 0, rs_1 = 0, rs_2 = 0;   /* stores so far; ring_n when tile t-2 / t-1 / t began */
+        bool ovf = false;                     /* more than 32 stores inside the window: every verdict counts as stale */
+        bar_sync(LZ4T_BAR_FULL(0), 64); out &= ~1u;
+        const smem_addr_t vda = smem_addr(tm->vd);
         for (;;) {
-          const u32 pk = __shfl_sync(FULLMASK, t_pack, li);
-          const u32 prs = __shfl_sync(FULLMASK, t_peers, li);
-          if (prs & tM & ((1u << li) - 1u)) {                               /* candidate was inserted inside this tile */
-            LZ4_TILE_COMMIT(tM);
-            scalar_post = true;
-            break;
-          }
-          tM |= 1u << li;                                                   /* lz4.c:1291: ip goes into the table, hit or not */
-          if (!(pk & 1u)) { LZ4_TILE_COMMIT(tM); ip++; break; }             /* lz4.c:1298; on to the search below */
+          const u32 e = (u32)(32 * t + li);
+          u32 pk, h;
+          smem_ld_u32x2(vda, (e & (LZ4T_RING - 1)) << 3, pk, h);
+          const u32 h2 = smem_ld_u32(vda, (((e - 2u) & (LZ4T_RING - 1)) << 3) + 4u);
+          LZ4_TPUT(h2, ip - 2);                                            /* every lane the same word: no hand-off between lanes */
+          if (ring_n - rs_lo >= 32) ovf = true;
+          if (lane == (ring_n & 31)) ring_h = h2;
+          ring_n++;
+          const unsigned stale = __ballot_sync(FULLMASK, ring_h == h);
+          if (stale || ovf || pk == LZ4T_END) { LZ4T_DBG(g_dbg_lz4t_stale); scalar_post = true; break; }      /* the plain probe below looks this one up itself */
+          LZ4_TPUT(h, ip);                                                 /* lz4.c:1291: ip goes into the table, hit or not */
+          if (ring_n - rs_lo >= 32) ovf = true;
+          if (lane == (ring_n & 31)) ring_h = h;
+          ring_n++;
+          if (!(pk & 1u)) { LZ4T_DBG(g_dbg_lz4t_x[0]); ip++; break; }                                 /* lz4.c:1298; on to the search below */
           const int off = (int)(pk >> 8);
           int mc = (int)((pk >> 2) & 15u);
-          if (mc == 13) {
-            mc = 13 + lz4_count_tail(sb, s, ip + 17, ip - off + 17, matchlimit, n);   /* ip+64 <= n: far from matchlimit */
-            if (mc >= 15 + 255) {                                           /* very long match: general emission below */
-              LZ4_TILE_COMMIT(tM);
+          if (mc == LZ4T_LONG) {
+            LZ4T_DBG(g_dbg_lz4t_x[1]);
+            mc = LZ4T_LONG + lz4_count_tail(sb, s, ip + 4 + LZ4T_LONG, ip - off + 4 + LZ4T_LONG, matchlimit, n);   /* ip+64 <= n: far from matchlimit */
+            if (mc >= 15 + 255) {                                          /* very long match: general emission below */
               hit = true; imm = true; match = ip - off;
               have_mc = true; mc_carry = mc;
+              LZ4T_DBG(g_dbg_lz4t_x[2]);
               break;
             }
           }
@@ -351,36 +409,42 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
            * grows inside a chain, so the check is made once per parked batch, before anything is
            * written (LZ4_FLUSH_CHECKED) */
           const bool ext = mc >= 15;
+          LZ4T_DBG(g_dbg_lz4t_seqs);
           if (lane == nrec) { rec = (ext ? 15u | ((u32)(mc - 15) << 24) : (u32)mc) | ((u32)off << 8); recop = op; }
           nrec++;
           op += ext ? 4 : 3;
           ip += mc + 4;
           li += mc + 4;
           anchor = ip;
-          if (ip + 64 > n) {                                                /* a match ended close to the end of the stream */
-            LZ4_TILE_COMMIT(tM);
-            if (ip >= mfl1) finished = true;                                /* lz4.c:1230-1233 */
-            else scalar_post = true;                                        /* the plain probe below takes over */
+          if (ip + 64 > n) {                                               /* a match ended close to the end of the stream */
+            if (ip >= mfl1) finished = true;                               /* lz4.c:1230-1233 */
+            else scalar_post = true;                                       /* the plain probe below takes over */
             break;
           }
-          if (li >= 64) { LZ4_TILE_COMMIT(tM); reanchor = true; break; }    /* jumped over the next tile */
-          if (li >= 32) {                                                   /* on to the next tile */
-            u32 carry = 0;
-            if (li - 2 < 32) tM |= 1u << (li - 2); else carry = 1u << (li - 34);   /* lz4.c:1236: start-2 goes into the table */
-            LZ4_TILE_COMMIT(tM);
+          if (li >= 128) { LZ4T_DBG(g_dbg_lz4t_x[3]); reanchor = true; break; }                       /* jumped past everything that is being prepared */
+          while (li >= 32) {                                               /* on to the next tile */
+            __threadfence_block();
+            bar_arrive(LZ4T_BAR_GO(t % 3), 64); out |= 1u << (t % 3);      /* its preparer may start tile t+3 */
+            t++; li -= 32;
+            rs_lo = rs_1; rs_1 = rs_2; rs_2 = ring_n;                      /* the window is now the stores of tiles t-2 .. t */
+            {
+              const int k = ring_n - 1 - ((ring_n - 1 - lane) & 31);       /* index of the store this lane holds */
+              if (ring_n == 0 || k < rs_lo) ring_h = 0xffffffffu;
+              ovf = ring_n - rs_lo > 32;
+            }
+            bar_sync(LZ4T_BAR_FULL(t % 3), 64); out &= ~(1u << (t % 3));
             if (nrec >= 24) LZ4_FLUSH_CHECKED();
-            w0 += 32; li -= 32; tM = carry;
-            LZ4_TILE_LOAD();
-          } else tM |= 1u << (li - 2);
+          }
         }
-#undef LZ4_TILE_COMMIT
-#undef LZ4_TILE_LOAD
+        /* leave the session: take the tiles that are still being prepared, so that every preparer is
+         * parked at its GO barrier again */
+        for (int i = 0; i < 3; i++)
+          if (out & (1u << i)) bar_sync(LZ4T_BAR_FULL(i), 64);
         if (finished) break;
         if (reanchor) continue;
       }
-      if (scalar_post) {
-#else
-      if (post && ip + 64 <= n) {
+      if (!TEAM && post && ip + 64 <= n) {
+        scalar_post = false;
         /* ---- chained "test next position" on the lane-cached window: stays in this loop for as
          * long as every match is immediately followed by another one ---- */
         bool room = true;
@@ -448,8 +512,8 @@ DEV int lz4_encode_warp(const u8* __restrict__ s, const int n, u8* __restrict__ 
           if (ip >= mfl1) break;                                             /* lz4.c:1230-1233 */
           continue;                                                          /* post stays true: the plain probe below takes over */
         }
-      } else if (post) {
-#endif
+      }
+      if (scalar_post) {
         /* ---- fill table at ip-2, test position ip (lz4.c:1236-1294); no literals on a hit ---- */
         u32 b0, b1, b2 = 0;
         const bool wide = ip + 14 <= n;

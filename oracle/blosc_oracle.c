@@ -422,6 +422,172 @@ last_literals:                                                  /* :1302-1329 */
 #undef TPUT
 }
 
+/* ------------------------------------------------------------------------- */
+/* LZ4, segment-parallel parse (NOT the reference's parse: the specification of the library's  */
+/* opt-in BLOSC_B200_PARSE=segmented mode, restated here so the GPU output can be checked byte  */
+/* for byte and so that tests can hand it to the reference's decoder)                           */
+/* ------------------------------------------------------------------------- */
+/* A stream of n bytes is cut into segments of seg_bytes.  Every segment is parsed on its own by the
+ * greedy loop of LZ4_compress_fast above with these differences:
+ *   - the hash table starts empty and is warmed with every position of the `warm` bytes in front
+ *     of the segment (ascending, so the most recent position of a hash wins); matches may reach
+ *     back into earlier segments (the usual 64 KiB window), never forward;
+ *   - the end-of-block rules (last match starts >= 12 bytes before the end, ends >= 5 bytes before
+ *     it, lz4.c:954-955) are applied to the segment end as well as to the stream end;
+ *   - the literals in front of the first match and after the last one are not encoded by the
+ *     segment: it reports their counts (lit0, tail) and the bytes in between (`body`: offset and
+ *     length bytes of the first match, then whole sequences).  A segment whose body does not fit a
+ *     slot of its own size under the reference's limitedOutput checks counts as "no match".
+ * The stream is the LZ4 encoding of the concatenated sequences: the tail of a segment (and whole
+ * match-less segments) become part of the literal run of the next first match, and one final
+ * literal run ends the block.  Any LZ4 decoder reads it; it is not the reference's byte stream. */
+typedef struct { int lit0, tokml, body, tail; } orc_segmeta;
+
+static int lz4_parse_segment(const uint8_t* s, int64_t n, int64_t b, int64_t e, int accel, int byU16, int64_t warm,
+                             uint8_t* d, int64_t olimit, orc_segmeta* m) {
+  uint32_t tab[4096];
+  uint16_t tab16[8192];
+  int64_t ip, anchor = b, op = 0, mflimitPlusOne, matchlimit, match, token = -1, q;
+  uint32_t forwardH;
+  int first = 1;
+  m->lit0 = -1; m->tokml = 0; m->body = 0; m->tail = (int)(e - b);
+  memset(tab, 0, sizeof tab);
+  memset(tab16, 0, sizeof tab16);
+#define TGET(h) (byU16 ? (int64_t)tab16[h] : (int64_t)tab[h])
+#define TPUT(h, v) do { if (byU16) tab16[h] = (uint16_t)(v); else tab[h] = (uint32_t)(v); } while (0)
+  for (q = b - warm > 0 ? b - warm : 0; q < b; q++)
+    if (q + 8 <= n) TPUT(lz4_hash(s + q, byU16), q);
+  mflimitPlusOne = e - LZ4_MFLIMIT + 1;
+  matchlimit = e < n - LZ4_LASTLITERALS ? e : n - LZ4_LASTLITERALS;
+  if (e - b < LZ4_MFLIMIT + 1) return 0;
+  TPUT(lz4_hash(s + b, byU16), b);
+  ip = b + 1;
+  forwardH = lz4_hash(s + ip, byU16);
+  for (;;) {
+    {
+      int64_t forwardIp = ip;
+      int step = 1, searchMatchNb = accel << 6;
+      for (;;) {
+        uint32_t h = forwardH;
+        int64_t current = forwardIp, matchIndex = TGET(h);
+        ip = forwardIp;
+        forwardIp += step;
+        step = searchMatchNb++ >> 6;
+        if (forwardIp > mflimitPlusOne) goto done;
+        forwardH = lz4_hash(s + forwardIp, byU16);
+        TPUT(h, current);
+        if (!byU16 && matchIndex + LZ4_MAXDIST < current) continue;
+        if (ld32(s + matchIndex) == ld32(s + ip)) { match = matchIndex; break; }
+      }
+    }
+    while (ip > anchor && match > 0 && s[ip - 1] == s[match - 1]) { ip--; match--; }
+    {
+      int64_t lit = ip - anchor;
+      if (first) {                                              /* counted, not stored */
+        if (op + (2 + 1 + LZ4_LASTLITERALS) > olimit) return -1;
+        m->lit0 = (int)lit;
+      } else {
+        token = op++;
+        if (op + lit + (2 + 1 + LZ4_LASTLITERALS) + lit / 255 > olimit) return -1;
+        if (lit >= 15) {
+          int64_t len = lit - 15;
+          d[token] = 15 << 4;
+          for (; len >= 255; len -= 255) d[op++] = 255;
+          d[op++] = (uint8_t)len;
+        } else d[token] = (uint8_t)(lit << 4);
+        memcpy(d + op, s + anchor, (size_t)lit);
+        op += lit;
+      }
+    }
+  next_match:
+    {
+      int64_t off = ip - match, mc = 0, p = ip + 4, r = match + 4;
+      d[op++] = (uint8_t)off; d[op++] = (uint8_t)(off >> 8);
+      while (p < matchlimit && s[p] == s[r]) { p++; r++; mc++; }
+      ip += mc + 4;
+      if (op + (1 + LZ4_LASTLITERALS) + (mc + 240) / 255 > olimit) return -1;
+      if (mc >= 15) {
+        if (first) m->tokml = 15; else d[token] += 15;
+        mc -= 15;
+        for (; mc >= 255; mc -= 255) d[op++] = 255;
+        d[op++] = (uint8_t)mc;
+      } else if (first) m->tokml = (int)mc;
+      else d[token] += (uint8_t)mc;
+      first = 0;
+    }
+    anchor = ip;
+    if (ip >= mflimitPlusOne) break;
+    TPUT(lz4_hash(s + ip - 2, byU16), ip - 2);
+    {
+      uint32_t h = lz4_hash(s + ip, byU16);
+      int64_t current = ip, matchIndex = TGET(h);
+      TPUT(h, current);
+      if ((byU16 || matchIndex + LZ4_MAXDIST >= current) && ld32(s + matchIndex) == ld32(s + ip)) {
+        token = op++;
+        d[token] = 0;
+        match = matchIndex;
+        goto next_match;
+      }
+    }
+    forwardH = lz4_hash(s + (++ip), byU16);
+  }
+done:
+  if (first) return 0;                                          /* no match in this segment */
+  m->body = (int)op;
+  m->tail = (int)(e - anchor);
+  return 1;
+#undef TGET
+#undef TPUT
+}
+
+static int64_t lz4_put_litlen(uint8_t* d, int64_t op, int64_t lit, int tokml) {
+  d[op++] = (uint8_t)(((lit >= 15 ? 15 : lit) << 4) | tokml);
+  if (lit >= 15) {
+    int64_t len = lit - 15;
+    for (; len >= 255; len -= 255) d[op++] = 255;
+    d[op++] = (uint8_t)len;
+  }
+  return op;
+}
+
+/* returns the compressed size, or 0 when it would not fit in cap */
+int orc_lz4_compress_segmented(const char* source, char* dest, int n, int cap, int accel, int seg_bytes, int warm) {
+  const uint8_t* s = (const uint8_t*)source;
+  uint8_t* d = (uint8_t*)dest;
+  uint8_t* body;
+  const int byU16 = n < 65536 + LZ4_MFLIMIT - 1;
+  int64_t b, op = 0, carry = 0, need;
+  if (accel < 1) accel = 1;
+  if (accel > 65537) accel = 65537;
+  if (n <= 0 || seg_bytes < 64) return 0;
+  body = (uint8_t*)malloc((size_t)seg_bytes + 64);
+  if (!body) return 0;
+  for (b = 0; b < n; b += seg_bytes) {
+    const int64_t e = b + seg_bytes < n ? b + seg_bytes : n;
+    orc_segmeta m;
+    const int r = lz4_parse_segment(s, n, b, e, accel, byU16, warm, body, e - b, &m);
+    if (r <= 0) { carry += e - b; continue; }
+    {
+      const int64_t lit = carry + m.lit0;
+      need = op + 1 + (lit >= 15 ? (lit - 15) / 255 + 1 : 0) + lit + m.body;
+      if (need > cap) { free(body); return 0; }
+      op = lz4_put_litlen(d, op, lit, m.tokml);
+      memcpy(d + op, s + b - carry, (size_t)lit); op += lit;
+      memcpy(d + op, body, (size_t)m.body); op += m.body;
+      carry = m.tail;
+    }
+  }
+  need = op + 1 + (carry >= 15 ? (carry - 15) / 255 + 1 : 0) + carry;
+  free(body);
+  if (need > cap) return 0;
+  op = lz4_put_litlen(d, op, carry, 0);
+  memcpy(d + op, s + n - carry, (size_t)carry); op += carry;
+  return (int)op;
+}
+
+static int g_lz4_seg_bytes = 0, g_lz4_seg_warm = 0;   /* 0: the reference's parse */
+void orc_set_lz4_segmented(int seg_bytes, int warm) { g_lz4_seg_bytes = seg_bytes; g_lz4_seg_warm = warm; }
+
 /* LZ4_decompress_safe (lz4.c:2451-2456): full-block decode, no dictionary.  The accept /
  * reject rules below are those of the "safe" decode loop (lz4.c:2234-2436); the fast
  * loop (:2077-2230) only ever handles sequences far from both buffer ends and applies
@@ -552,8 +718,10 @@ static int orc_block_c(const orc_ctx* c, int32_t bsize, int leftoverblock, int32
     if (c->compcode == ORC_BLOSCLZ)
       cbytes = orc_blosclz_compress(c->clevel, in + j * neblock, neblock, dest, maxout, !dont_split);
     else if (c->compcode == ORC_LZ4)
-      cbytes = orc_lz4_compress_fast((const char*)in + j * neblock, (char*)dest, neblock, maxout,
-                                     10 - c->clevel);
+      cbytes = g_lz4_seg_bytes ? orc_lz4_compress_segmented((const char*)in + j * neblock, (char*)dest, neblock, maxout,
+                                                            10 - c->clevel, g_lz4_seg_bytes, g_lz4_seg_warm)
+                               : orc_lz4_compress_fast((const char*)in + j * neblock, (char*)dest, neblock, maxout,
+                                                       10 - c->clevel);
     else return -5;
     if (cbytes > maxout) return -1;
     if (cbytes < 0) return -2;

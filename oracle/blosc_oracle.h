@@ -46,6 +46,9 @@ int orc_blosclz_decompress(const void* input, int length, void* output, int maxo
 int orc_lz4_compress_fast(const char* src, char* dst, int srcSize, int dstCapacity,
                           int acceleration);
 /* internal-complibs/lz4-1.10.0/lz4.c:2451-2456 -> 2022-2445 */
+/* the library's opt-in segment-parallel parse, restated (not the reference's byte stream; any LZ4 decoder reads it) */
+int orc_lz4_compress_segmented(const char* src, char* dst, int srcSize, int dstCapacity, int acceleration, int seg_bytes, int warm);
+void orc_set_lz4_segmented(int seg_bytes, int warm);   /* orc_compress_ctx uses it for LZ4 when seg_bytes != 0 */
 int orc_lz4_decompress_safe(const char* src, char* dst, int compressedSize, int dstCapacity);
 
 /* ---- chunk framing (blosc/blosc.c) ---- */

@@ -74,7 +74,23 @@ int b2_launch_filter(const FilterArgs* a, b2_stream_t) {
   return 0;
 }
 
+static int g_lz4_team = 1;
+void emu_set_lz4_team(int on) { g_lz4_team = on; }
+void emu_lz4t_counters(long long* c) { c[0] = g_dbg_lz4t_sessions; c[1] = g_dbg_lz4t_seqs; c[2] = g_dbg_lz4t_stale; for (int i = 0; i < 4; i++) c[3 + i] = g_dbg_lz4t_x[i]; }
+
 int b2_launch_encode(const EncodeArgs* a, b2_stream_t) {
+  if (g_lz4_team && a->codec == B2_CODEC_LZ4 && a->table_bytes == LZ4_TABLE_BYTES) {
+    int ctas = a->map.nstreams;
+    if (ctas > 3) ctas = 3;          /* few CTAs: every team goes through several streams */
+    if (ctas <= 0) return 0;
+    g_launches++;
+    EncodeArgs args = *a;
+    args.num_sms = 2;
+    args.queue_base = *a->queue_base_host;
+    *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas;
+    simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(TEAM_WARPS * 32), TEAM_SMEM_BYTES, [&] { encode_team_kernel(args); });
+    return 0;
+  }
   int wpc = 65536 / a->table_bytes;
   if (wpc > 4) wpc = 4;
   if (wpc < 1) wpc = 1;
@@ -131,6 +147,27 @@ int emu_lz4_encode(const unsigned char* src, int n, unsigned char* dst, int cap,
     if (g_lz4_pack && n >= LZ4_TAB17_MINLEN && n <= LZ4_TAB17_MAXLEN) r = lz4_encode_warp<false, true>(src, n, dst, cap, accel, simt::g_dynsmem, &need);
     else r = n < 65536 + LZ4_MFLIMIT - 1 ? lz4_encode_warp<true>(src, n, dst, cap, accel, simt::g_dynsmem, &need)
                                         : lz4_encode_warp<false>(src, n, dst, cap, accel, simt::g_dynsmem, &need);
+    if ((threadIdx.x & 31) == 3) g_last_need = need;
+    if ((threadIdx.x & 31) == 7) result = r;
+  });
+  return result;
+}
+/* the same stream through a whole team (walker + three preparers) */
+int emu_lz4_encode_team(const unsigned char* src, int n, unsigned char* dst, int cap, int accel, int walker) {
+  int result = 0;
+  simt::launch(simt::Dim3(1), simt::Dim3(TEAM_WARPS * 32), TEAM_SMEM_BYTES, [&] {
+    unsigned char* smem = simt::g_dynsmem;
+    Lz4Team* tm = (Lz4Team*)(smem + LZ4_TABLE_BYTES);
+    const int warp = (int)(threadIdx.x >> 5);
+    if (threadIdx.x == 0) { tm->cmd = 0; tm->gen = 0; }
+    __syncthreads();
+    if (warp != walker) { lz4_team_preparer(tm, smem, (warp - walker - 1) & 3); return; }
+    int need = 0;
+    int r = n < 65536 + LZ4_MFLIMIT - 1 ? lz4_encode_warp<true, false, true>(src, n, dst, cap, accel, smem, &need, tm)
+                                        : lz4_encode_warp<false, false, true>(src, n, dst, cap, accel, smem, &need, tm);
+    if ((threadIdx.x & 31) == 0) *(volatile int*)&tm->cmd = LZ4T_QUIT;
+    __syncwarp();
+    bar_arrive(LZ4T_BAR_GO(0), 64); bar_arrive(LZ4T_BAR_GO(1), 64); bar_arrive(LZ4T_BAR_GO(2), 64);
     if ((threadIdx.x & 31) == 3) g_last_need = need;
     if ((threadIdx.x & 31) == 7) result = r;
   });

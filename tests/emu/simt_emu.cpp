@@ -52,6 +52,22 @@ void cta_barrier() {
   to_scheduler();
 }
 
+/* named barriers (PTX bar.sync / bar.arrive with an explicit thread count): arrivals are counted per
+ * barrier id; when `count` threads have arrived the waiting ones are released and the barrier resets. */
+static int g_bar_arrived[16];
+static int g_bar_expect[16];
+void named_barrier(int id, int count, bool wait) {
+  if (id < 1 || id > 15) { fprintf(stderr, "simt: bad barrier id %d\n", id); abort(); }
+  if (g_bar_expect[id] && g_bar_expect[id] != count) { fprintf(stderr, "simt: barrier %d used with counts %d and %d\n", id, g_bar_expect[id], count); abort(); }
+  g_bar_expect[id] = count;
+  g_bar_arrived[id]++;
+  if (wait) {
+    cur->st = WAIT_BAR;
+    cur->arg = id;
+    to_scheduler();
+  }
+}
+
 static void resolve_warp(Thread* th, unsigned base, unsigned nlanes, bool* did) {
   /* find a waiting lane; its mask names the participants */
   for (unsigned l0 = 0; l0 < nlanes; l0++) {
@@ -124,6 +140,7 @@ void launch(Dim3 grid, Dim3 block, size_t dynsmem, const std::function<void()>& 
     for (unsigned by = 0; by < grid.y; by++)
       for (unsigned bx = 0; bx < grid.x; bx++) {
         g_blockIdx = Dim3(bx, by, bz);
+        memset(g_bar_arrived, 0, sizeof g_bar_arrived); memset(g_bar_expect, 0, sizeof g_bar_expect);
         memset(smem.data(), 0xCD, smem.size());
         g_dynsmem = (unsigned char*)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
         for (unsigned i = 0; i < nthreads; i++) {
@@ -154,6 +171,15 @@ void launch(Dim3 grid, Dim3 block, size_t dynsmem, const std::function<void()>& 
           bool did = false;
           for (unsigned base = 0; base < nthreads; base += 32)
             resolve_warp(th.data(), base, nthreads - base < 32 ? nthreads - base : 32, &did);
+          for (int b = 1; b < 16; b++) {
+            if (g_bar_expect[b] && g_bar_arrived[b] >= g_bar_expect[b]) {
+              if (g_bar_arrived[b] > g_bar_expect[b]) { fprintf(stderr, "simt: barrier %d over-subscribed (%d of %d)\n", b, g_bar_arrived[b], g_bar_expect[b]); abort(); }
+              for (unsigned i = 0; i < nthreads; i++)
+                if (th[i].st == WAIT_BAR && th[i].arg == b) th[i].st = RUNNABLE;
+              g_bar_arrived[b] = 0; g_bar_expect[b] = 0;
+              did = true;
+            }
+          }
           unsigned waiting_cta = 0;
           for (unsigned i = 0; i < nthreads; i++) waiting_cta += th[i].st == WAIT_CTA;
           if (alive && waiting_cta == alive) {

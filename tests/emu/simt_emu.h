@@ -25,7 +25,7 @@ struct Dim3 {
   Dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 
-enum State { RUNNABLE, WAIT_WARP, WAIT_CTA, DONE };
+enum State { RUNNABLE, WAIT_WARP, WAIT_CTA, WAIT_BAR, DONE };
 enum Op { OP_NONE, OP_SYNCWARP, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_MATCH_ANY };
 
 struct Thread {
@@ -48,6 +48,7 @@ extern unsigned long long g_collectives;
 
 uint64_t warp_collective(Op op, unsigned mask, uint64_t val, int arg);
 void cta_barrier();
+void named_barrier(int id, int count, bool wait);   /* bar.sync / bar.arrive id, count (count = THREADS expected) */
 void launch(Dim3 grid, Dim3 block, size_t dynsmem, const std::function<void()>& body);
 
 }  // namespace simt
@@ -98,6 +99,7 @@ template <typename T> static inline unsigned __match_any_sync(unsigned m, T v) {
 }
 static inline void __syncwarp(unsigned m = 0xffffffffu) { simt::warp_collective(simt::OP_SYNCWARP, m, 0, 0); }
 static inline void __syncthreads() { simt::cta_barrier(); }
+static inline void __nanosleep(unsigned) {}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 

@@ -66,6 +66,43 @@ typedef struct EncodeArgs {
   ScanArgs scan;
 } EncodeArgs;
 
+/* ---- segment-parallel LZ4 parse (dev_lz4fast.cuh) ---- */
+#define B2_FAST_SEG 1024    /* bytes per segment (dev_lz4fast.cuh FAST_SEG) */
+typedef struct FastSeg {   /* one record per segment of FAST_SEG bytes */
+  uint16_t nbytes;         /* bytes in the segment's slot (0: no match, the segment is all literals) */
+  uint16_t l1;             /* literals in front of the segment's first match */
+  uint16_t tail;           /* literals after its last match (the whole segment when nbytes == 0) */
+  uint16_t lt;             /* slot position of the last sequence's token */
+  uint16_t lm, lo;         /* length and offset of the last match (its length bytes are not in the slot) */
+  uint16_t pad0, pad1;
+  uint32_t dst;            /* by the stream scan: offset of the merged output inside the stream's LZ4 block,
+                            * 0xffffffff when the segment only continues the previous segment's last match */
+  uint32_t pin;            /* by the stream scan: literals pending in front of this segment */
+  uint32_t run;            /* by the stream scan: final length of the last match (with the segments it swallowed) */
+  uint32_t pad2;
+} FastSeg;
+
+typedef struct FastArgs {
+  StreamMap map;
+  const uint8_t* in;       /* filtered (or original) bytes, block-major */
+  uint8_t* slots;
+  uint16_t* prev;          /* [nbytes] hash-chain index written by index_kernel */
+  FastSeg* segs;           /* stream-major: stream idx starts at idx * segs_full (the leftover stream comes last) */
+  int* seg_done;           /* [nstreams] zero-initialised count of parsed groups; the warp that completes a stream scans it */
+  int* ptail;              /* [nstreams] literals after the stream's last match */
+  int* csizes;
+  int* needs;
+  int segs_full, segs_left;        /* segments per full stream / of the leftover stream */
+  int groups_full, groups_left;    /* groups of 32 segments (one warp each) */
+  int depth, accel;
+  int* queue;
+  unsigned queue_base;
+  unsigned* queue_base_host;
+  int* done;
+  int fold_scan;
+  ScanArgs scan;
+} FastArgs;
+
 typedef struct CompactArgs {
   StreamMap map;
   const uint8_t* in;     /* raw splits are copied from here */
@@ -76,6 +113,9 @@ typedef struct CompactArgs {
   uint8_t* dest;
   uint32_t hdr0;         /* version | versionlz<<8 | flags<<16 | typesize<<24 */
   int nbytes32, nblocks;
+  const FastSeg* segs;   /* non-NULL: the compressed streams are fast-parsed segments to be stitched (dev_lz4fast.cuh) */
+  const int* ptail;
+  int segs_full, segs_left;
 } CompactArgs;
 
 typedef struct DecodeArgs {

@@ -47,9 +47,10 @@ int  b2_launch_encode(const EncodeArgs* a, b2_stream_t s);
 int  b2_launch_scan(const ScanArgs* a, b2_stream_t s);
 int  b2_launch_compact(const CompactArgs* a, b2_stream_t s);
 int  b2_launch_decode(const DecodeArgs* a, b2_stream_t s);
+int  b2_launch_fast(const FastArgs* a, b2_stream_t s);      /* index_kernel + parse_kernel (segment-parallel LZ4) */
 
 /* profiling: per-kernel-kind CUDA-event timing (off by default) */
-enum { B2_K_FILTER = 0, B2_K_ENCODE, B2_K_SCAN, B2_K_COMPACT, B2_K_DECODE, B2_K_UNFILTER, B2_K_COUNT };
+enum { B2_K_FILTER = 0, B2_K_ENCODE, B2_K_SCAN, B2_K_COMPACT, B2_K_DECODE, B2_K_UNFILTER, B2_K_INDEX, B2_K_PARSE, B2_K_COUNT };
 void b2_prof_enable(int on);
 void b2_prof_reset(void);
 int  b2_prof_get(int kind, double* ms_total, long long* launches);

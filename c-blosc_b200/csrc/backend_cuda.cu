@@ -55,6 +55,7 @@ extern "C" int b2_device_prepare(void) {
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_BLOSCLZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZSTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
+  CK(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_WARPS * FAST_TAB_BYTES));
   CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
   return 0;
 }
@@ -209,6 +210,30 @@ extern "C" int b2_launch_encode(const EncodeArgs* a, b2_stream_t s) {
   *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas * (unsigned)wpc;
   encode_kernel<<<ctas, wpc * 32, (size_t)wpc * a->table_bytes, s->s>>>(args);
   CK(cudaGetLastError());
+  return 0;
+}
+
+/* segment-parallel LZ4: the hash-chain index of every stream, then one lane per segment */
+extern "C" int b2_launch_fast(const FastArgs* a, b2_stream_t s) {
+  if (a->map.nstreams <= 0) return 0;
+  {
+    int ctas = (a->map.nstreams + INDEX_WARPS - 1) / INDEX_WARPS;
+    ProfScope ps(B2_K_INDEX, s->s);
+    index_kernel<<<ctas, INDEX_WARPS * 32, INDEX_WARPS * FAST_TAB_BYTES, s->s>>>(*a);
+    CK(cudaGetLastError());
+  }
+  {
+    const long long njobs = (long long)a->map.nfull * a->map.nsplits * a->groups_full + a->groups_left;
+    long long ctas = (njobs + PARSE_WARPS - 1) / PARSE_WARPS;
+    const long long cap = (long long)num_sms() * 16;
+    if (ctas > cap) ctas = cap;
+    ProfScope ps(B2_K_PARSE, s->s);
+    FastArgs args = *a;
+    args.queue_base = *a->queue_base_host;
+    *a->queue_base_host += (unsigned)njobs + (unsigned)ctas * PARSE_WARPS;
+    parse_kernel<<<(unsigned)ctas, PARSE_WARPS * 32, 0, s->s>>>(args);
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 

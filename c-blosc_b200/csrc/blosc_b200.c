@@ -131,6 +131,7 @@ typedef struct {
   int in_use, ready, dev;
   b2_stream_t stream;
   b2_buf in, filt, slots, out, csizes, needs, bstarts;
+  b2_buf prev, segs, seg_done, ptail;   /* segment-parallel LZ4 parse (dev_lz4fast.cuh) */
   int* d_result;        /* B2_R_* words (b2_args.h): cbytes, fits, status, work-queue and done counters */
   int* h_result;        /* pinned mirror */
   unsigned queue_base;  /* tickets drawn from the B2_R_QUEUE counter so far (dev_chunk.cuh next_stream) */
@@ -163,6 +164,7 @@ static void ws_teardown(b2_ws* w) {
   int k;
   buf_free(&w->in); buf_free(&w->filt); buf_free(&w->slots); buf_free(&w->out);
   buf_free(&w->csizes); buf_free(&w->needs); buf_free(&w->bstarts);
+  buf_free(&w->prev); buf_free(&w->segs); buf_free(&w->seg_done); buf_free(&w->ptail);
   for (k = 0; k < B2_STAGE_DEPTH; k++) {
     if (w->stage[k]) b2_pinned_free(w->stage[k]);
     if (w->stage_ev[k]) b2_event_destroy(w->stage_ev[k]);
@@ -180,6 +182,7 @@ static void ws_teardown(b2_ws* w) {
 static void ws_reset_counters(b2_ws* w) {
   b2_stream_sync(w->stream);
   b2_memset_dev(w->d_result, 0, 4 * B2_R_WORDS, w->stream);
+  if (w->seg_done.p) b2_memset_dev(w->seg_done.p, 0, w->seg_done.cap, w->stream);
   b2_stream_sync(w->stream);
   w->queue_base = 0;
 }
@@ -244,6 +247,13 @@ static int buf_ensure(b2_buf* b, size_t need) {
   return 0;
 }
 
+/* a buffer of counters that the kernels leave at zero: cleared only when it is (re)allocated */
+static int buf_ensure_zeroed(b2_ws* w, b2_buf* b, size_t need) {
+  if (need <= b->cap) return 0;
+  if (buf_ensure(b, need)) return -1;
+  return b2_memset_dev(b->p, 0, b->cap, w->stream);
+}
+
 int blosc_free_resources(void) {                              /* blosc.h:411 */
   int i;
   pthread_mutex_lock(&g_ws_mutex);
@@ -252,6 +262,7 @@ int blosc_free_resources(void) {                              /* blosc.h:411 */
     if (w->in_use || !w->ready) continue;
     buf_free(&w->in); buf_free(&w->filt); buf_free(&w->slots); buf_free(&w->out);
     buf_free(&w->csizes); buf_free(&w->needs); buf_free(&w->bstarts);
+    buf_free(&w->prev); buf_free(&w->segs); buf_free(&w->seg_done); buf_free(&w->ptail);
   }
   pthread_mutex_unlock(&g_ws_mutex);
   return 0;
@@ -503,6 +514,14 @@ static int lz4_pack_wanted(const b2_place* pl) {
   return e && *e && atoi(e) != 0;
 }
 
+/* BLOSC_B200_PARSE selects the LZ4 encoder: "exact" (default) replays LZ4_compress_fast bit for bit, chunks are
+ * byte-identical to the reference's; "fast" (alias "segmented") is the segment-parallel parser of dev_lz4fast.cuh:
+ * chunks are valid Blosc-1 / LZ4 that any reference build decodes, but not the reference's bytes. */
+static int lz4_fast_wanted(void) {
+  const char* e = getenv("BLOSC_B200_PARSE");
+  return e && (strcmp(e, "fast") == 0 || strcmp(e, "segmented") == 0);
+}
+
 /* header + raw payload (blosc.c:825-830) */
 static int emit_memcpyed(const uint8_t* hdr, const void* src, int src_dev, void* dest, int dest_dev, int32_t nbytes) {
   b2_ws* w = NULL;
@@ -625,7 +644,25 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
     ea.fold_scan = nblocks <= B2_FOLD_SCAN_MAX_BLOCKS;
     ea.scan = sa;
     launched = 1;
-    if (b2_launch_encode(&ea, w->stream)) break;
+    memset(&ca, 0, sizeof ca);
+    if (ea.codec == B2_CODEC_LZ4 && lz4_fast_wanted()) {
+      FastArgs fx;
+      const int neblock = bs / nsplits;
+      memset(&fx, 0, sizeof fx);
+      fx.map = ea.map; fx.in = ea.in; fx.slots = ea.slots; fx.csizes = ea.csizes; fx.needs = ea.needs;
+      fx.segs_full = (neblock + B2_FAST_SEG - 1) / B2_FAST_SEG; fx.segs_left = (leftover + B2_FAST_SEG - 1) / B2_FAST_SEG;
+      fx.groups_full = (fx.segs_full + 31) / 32; fx.groups_left = (fx.segs_left + 31) / 32;
+      fx.depth = 3 * clevel + 1; fx.accel = ea.accel;
+      if (buf_ensure(&w->prev, 2 * (size_t)nb + 64)) break;
+      if (buf_ensure(&w->segs, ((size_t)nfull * nsplits * fx.segs_full + fx.segs_left + 8) * sizeof(FastSeg))) break;
+      if (buf_ensure_zeroed(w, &w->seg_done, (size_t)ea.map.nstreams * 4 + 64)) break;
+      if (buf_ensure(&w->ptail, (size_t)ea.map.nstreams * 4 + 64)) break;
+      fx.prev = (uint16_t*)w->prev.p; fx.segs = (FastSeg*)w->segs.p; fx.seg_done = (int*)w->seg_done.p; fx.ptail = (int*)w->ptail.p;
+      fx.queue = ea.queue; fx.queue_base_host = ea.queue_base_host; fx.done = ea.done;
+      fx.fold_scan = ea.fold_scan; fx.scan = sa;
+      if (b2_launch_fast(&fx, w->stream)) break;
+      ca.segs = fx.segs; ca.ptail = fx.ptail; ca.segs_full = fx.segs_full; ca.segs_left = fx.segs_left;
+    } else if (b2_launch_encode(&ea, w->stream)) break;
     if (!ea.fold_scan && b2_launch_scan(&sa, w->stream)) break;
     if (dest_dev && !pl) d_dest = (uint8_t*)dest;
     else { if (buf_ensure(&w->out, (size_t)dsz + 64)) break; d_dest = (uint8_t*)w->out.p; }

@@ -18,6 +18,7 @@
 #include "dev_common.cuh"
 #include "dev_inflate.cuh"
 #include "dev_lz4.cuh"
+#include "dev_lz4fast.cuh"
 #include "dev_zstd.cuh"
 
 
@@ -218,6 +219,85 @@ __global__ void __launch_bounds__(TEAM_WARPS * 32, TEAM_CTAS_PER_SM) encode_team
 }
 
 
+/* ---- segment-parallel LZ4 (dev_lz4fast.cuh): index_kernel, parse_kernel ---- */
+#define INDEX_WARPS 4
+/* one warp per stream, FAST_TAB_BYTES of shared memory each */
+__global__ void __launch_bounds__(INDEX_WARPS * 32) index_kernel(FastArgs a) {
+#ifdef SIMT_EMU
+  u8* smem = simt::g_dynsmem;
+#else
+  extern __shared__ __align__(16) u8 smem[];
+#endif
+  const int warp = (int)(threadIdx.x >> 5);
+  u32* tab = (u32*)(smem + (size_t)warp * FAST_TAB_BYTES);
+  for (int idx = (int)blockIdx.x * INDEX_WARPS + warp; idx < a.map.nstreams; idx += (int)gridDim.x * INDEX_WARPS) {
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    lz4f_index_warp(a.in + off, len, a.prev + off, tab);
+    __syncwarp();
+  }
+}
+
+#define PARSE_WARPS 4
+__global__ void __launch_bounds__(PARSE_WARPS * 32) parse_kernel(FastArgs a) {
+  const int lane = lane_id();
+  const int nfs = a.map.nfull * a.map.nsplits;
+  const int njobs = nfs * a.groups_full + a.groups_left;
+  int mine = 0;                                   /* streams completed (scanned) by this warp */
+  for (;;) {
+    int job = 0;
+    if (lane == 0) job = (int)((unsigned)atomicAdd(a.queue, 1) - a.queue_base);
+    job = __shfl_sync(FULLMASK, job, 0);
+    if (job >= njobs) break;
+    int idx, g, ngroups, K;
+    if (job < a.groups_left) { idx = nfs; g = job; ngroups = a.groups_left; K = a.segs_left; }
+    else {
+      /* split-major, as next_stream: the byte-planes that turn out to be hard start first */
+      const int j = job - a.groups_left;
+      const int per_split = a.map.nfull * a.groups_full;
+      const int s = j / per_split, r = j - s * per_split;
+      const int b = r / a.groups_full;
+      g = r - b * a.groups_full;
+      idx = b * a.map.nsplits + s; ngroups = a.groups_full; K = a.segs_full;
+    }
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    FastSeg* segs = a.segs + (long long)idx * a.segs_full;
+    const int k = g * 32 + lane;
+    if (k < K) {
+      const int sa = k * FAST_SEG, sb = sa + FAST_SEG < len ? sa + FAST_SEG : len;
+      lz4f_parse_lane(a.in + off, len, a.prev + off, sa, sb, a.slots + off + sa, &segs[k], a.depth, a.accel);
+    }
+    __syncwarp();
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(&a.seg_done[idx], 1) + 1 == ngroups;
+    last = __shfl_sync(FULLMASK, last, 0);
+    if (last) {
+      __threadfence();
+      int ptail = 0;
+      int c = lz4f_stream_scan(segs, K, len, &ptail);
+      if (c >= len) c = len;                       /* blosc.c:705-714: incompressible split is stored raw */
+      if (lane == 0) { a.csizes[idx] = c; a.needs[idx] = c; a.ptail[idx] = ptail; a.seg_done[idx] = 0; }
+      mine++;
+    }
+    __syncwarp();
+  }
+  if (mine == 0) return;
+  __threadfence();
+  int last = 0;
+  if (lane == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;
+  last = __shfl_sync(FULLMASK, last, 0);
+  if (!last) return;
+  __threadfence();
+  if (a.fold_scan) warp_scan_blocks(a.scan);
+  __syncwarp();
+  if (lane == 0) *a.done = 0;
+}
+
+
 #define SCAN_THREADS 1024
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
   __shared__ long long part[SCAN_THREADS];
@@ -307,7 +387,10 @@ __global__ void __launch_bounds__(COMPACT_THREADS) compact_kernel(CompactArgs a)
       stream_locate(a.map, idx, &blk, &off, &len, &sp);
       const int c = a.csizes[idx];
       if (tid == 0) st_u32_bytes(a.dest + pos, (u32)c);               /* blosc.c:715 */
-      cta_copy_bytes(a.dest + pos + 4, (c == len ? a.in : a.slots) + off, c);
+      if (a.segs && c != len)
+        lz4f_stitch_cta(a.dest + pos + 4, c, a.in + off, len, a.slots + off, a.segs + (long long)idx * a.segs_full,
+                        b < a.map.nfull ? a.segs_full : a.segs_left, a.ptail[idx]);
+      else cta_copy_bytes(a.dest + pos + 4, (c == len ? a.in : a.slots) + off, c);
       pos += 4 + c;
     }
   }

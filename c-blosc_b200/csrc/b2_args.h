@@ -67,7 +67,8 @@ typedef struct EncodeArgs {
 } EncodeArgs;
 
 /* ---- segment-parallel LZ4 parse (dev_lz4fast.cuh) ---- */
-#define B2_FAST_SEG 1024    /* bytes per segment (dev_lz4fast.cuh FAST_SEG) */
+#define B2_FAST_SEG 256     /* bytes per segment (dev_lz4fast.cuh FAST_SEG) */
+#define B2_FAST_WIN_MAX (128 * 1024)   /* bytes of a stream that one parse CTA keeps in shared memory */
 typedef struct FastSeg {   /* one record per segment of FAST_SEG bytes */
   uint16_t nbytes;         /* bytes in the segment's slot (0: no match, the segment is all literals) */
   uint16_t l1;             /* literals in front of the segment's first match */
@@ -93,7 +94,8 @@ typedef struct FastArgs {
   int* csizes;
   int* needs;
   int segs_full, segs_left;        /* segments per full stream / of the leftover stream */
-  int groups_full, groups_left;    /* groups of 32 segments (one warp each) */
+  int win_bytes;                   /* bytes per parse window (one CTA, one thread per segment): multiple of 32 segments */
+  int groups_full, groups_left;    /* windows per full stream / of the leftover stream */
   int depth, accel;
   int* queue;
   unsigned queue_base;

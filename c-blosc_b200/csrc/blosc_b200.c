@@ -651,7 +651,14 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
       memset(&fx, 0, sizeof fx);
       fx.map = ea.map; fx.in = ea.in; fx.slots = ea.slots; fx.csizes = ea.csizes; fx.needs = ea.needs;
       fx.segs_full = (neblock + B2_FAST_SEG - 1) / B2_FAST_SEG; fx.segs_left = (leftover + B2_FAST_SEG - 1) / B2_FAST_SEG;
-      fx.groups_full = (fx.segs_full + 31) / 32; fx.groups_left = (fx.segs_left + 31) / 32;
+      {
+        /* one parse CTA per window: the whole stream when it fits in B2_FAST_WIN_MAX, rounded up to whole warps of segments */
+        const int longest = neblock > leftover ? neblock : leftover;
+        int win = (longest + 32 * B2_FAST_SEG - 1) / (32 * B2_FAST_SEG) * (32 * B2_FAST_SEG);
+        if (win > B2_FAST_WIN_MAX) win = B2_FAST_WIN_MAX;
+        fx.win_bytes = win;
+        fx.groups_full = (neblock + win - 1) / win; fx.groups_left = (leftover + win - 1) / win;
+      }
       fx.depth = 3 * clevel + 1; fx.accel = ea.accel;
       if (buf_ensure(&w->prev, 2 * (size_t)nb + 64)) break;
       if (buf_ensure(&w->segs, ((size_t)nfull * nsplits * fx.segs_full + fx.segs_left + 8) * sizeof(FastSeg))) break;

@@ -46,15 +46,21 @@ struct FastView {
   const u32* w;      /* aligned word holding s[0] */
   int sal;           /* s - (const u8*)w */
   int nwords;        /* words that overlap the stream */
+  const u32* sm;     /* words [sm_lo, sm_hi) of the stream are also in shared memory, at sm[i - sm_lo] */
+  int sm_lo, sm_hi;
 };
 DEV FastView fast_view(const u8* s, int n) {
   FastView v;
   v.sal = (int)((uintptr_t)s & 3u);
   v.w = (const u32*)(s - v.sal);
   v.nwords = (n + v.sal + 3) >> 2;
+  v.sm = nullptr; v.sm_lo = 0; v.sm_hi = 0;
   return v;
 }
-DEV u32 fast_word(const FastView& v, int i) { return i < v.nwords ? __ldg(v.w + i) : 0u; }
+DEV u32 fast_word(const FastView& v, int i) {
+  if (i >= v.sm_lo && i < v.sm_hi) return v.sm[i - v.sm_lo];
+  return i < v.nwords ? __ldg(v.w + i) : 0u;
+}
 /* 4 bytes at position p (p >= 0); bytes past the end of the stream read as zero */
 DEV u32 fast_ld32(const FastView& v, int p) {
   const int q = p + v.sal;
@@ -70,19 +76,28 @@ DEV u32 fast_ld8(const FastView& v, int p) {
 
 DEV u32 fast_hash(u32 word, u32 b4) { return ((word * 2654435761u) ^ (b4 * 2246822519u)) >> (32 - FAST_HLOG); }
 
-/* ---- index: prev[p] for every position of one stream, by one warp ---- */
+/* ---- index: prev[p] for every position of one stream, by one warp ----
+ * Every step takes FAST_BATCH = 128 positions (4 consecutive ones per lane): hash, look the table up (state as of
+ * the end of the previous step), then enter the 128 positions (atomicMax: the highest position wins, whatever the
+ * order of the lanes).  The words of the next step are requested before this step's table work, so the only latency
+ * on the step-to-step chain is the shared-memory round trip. */
 DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict__ prev, u32* tab) {
   const int lane = lane_id();
   for (int i = lane; i < (1 << FAST_HLOG); i += 32) tab[i] = 0;
   __syncwarp();
   const FastView v = fast_view(s, n);
   const bool vec = (((uintptr_t)prev) & 7u) == 0;
+  const u32 sh = (u32)v.sal * 8u;
+  const int wi = lane;                            /* lane's first word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane */
+  u32 n0 = fast_word(v, wi), n1 = fast_word(v, wi + 1), n2 = fast_word(v, wi + 2);
   for (int base = 0; base < n; base += FAST_BATCH) {
     const int p0 = base + 4 * lane;
+    const u32 w0 = n0, w1 = n1, w2 = n2;
+    {
+      const int nx = ((base + FAST_BATCH) >> 2) + wi;
+      n0 = fast_word(v, nx); n1 = fast_word(v, nx + 1); n2 = fast_word(v, nx + 2);
+    }
     /* bytes p0 .. p0+7 */
-    const int q = p0 + v.sal;
-    const u32 w0 = fast_word(v, q >> 2), w1 = fast_word(v, (q >> 2) + 1), w2 = fast_word(v, (q >> 2) + 2);
-    const u32 sh = (u32)(q & 3) * 8u;
     const u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
     u32 h[4], c[4];
 #pragma unroll
@@ -90,6 +105,7 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
       const u32 word = __funnelshift_r(v0, v1, 8u * j);
       h[j] = fast_hash(word, (v1 >> (8u * j)) & 0xffu);
     }
+    const bool full = base + FAST_BATCH + 8 <= n;  /* every position of the step has its 8 bytes inside the stream */
     if (base == 0) {
       /* the first batch has nothing in front of it: resolve it position by position, so that a run or a
        * short period at the very start of a stream is found from its second occurrence on */
@@ -105,11 +121,19 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++) c[j] = (p0 + j + 8 <= n) ? tab[h[j]] : 0u;
+      for (int j = 0; j < 4; j++) c[j] = (full || p0 + j + 8 <= n) ? tab[h[j]] : 0u;
       __syncwarp();
+      /* a run (every position of the step hashes alike -- the zero planes of shuffled data) would make the
+       * 128 atomics collide on one word: the last position enters it alone */
+      const u32 hl = __shfl_sync(FULLMASK, h[3], 0);
+      const bool same = h[0] == h[1] && h[1] == h[2] && h[2] == h[3] && h[3] == hl;
+      if (full && __all_sync(FULLMASK, same)) {
+        if (lane == 31) tab[h[3]] = (u32)(p0 + 4);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (p0 + j + 8 <= n) atomicMax(&tab[h[j]], (u32)(p0 + j + 1));
+        for (int j = 0; j < 4; j++)
+          if ((full || p0 + j + 8 <= n) && (j == 3 || h[j] != h[j + 1])) atomicMax(&tab[h[j]], (u32)(p0 + j + 1));
+      }
       __syncwarp();
     }
     u32 d[4];
@@ -187,9 +211,8 @@ DEV int lz4f_search(const FastView& v, const u16* __restrict__ prev, const int i
  * LAST sequence has no match-length extension bytes: a match that ends exactly at the end of the segment may
  * be continued by the segments that follow (runs, periodic data), so its final length is only known to the
  * stream scan. */
-DEV void lz4f_parse_lane(const u8* __restrict__ s, const int n, const u16* __restrict__ prev, const int a, const int b,
+DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__ prev, const int a, const int b,
                          u8* __restrict__ slot, FastSeg* rec, const int depth, const int accel) {
-  const FastView v = fast_view(s, n);
   int mfl = b - 4, mlim = b;                     /* last position a match may start at; first byte it may not cover */
   if (mfl > n - FAST_MFLIMIT) mfl = n - FAST_MFLIMIT;
   if (mlim > n - FAST_LASTLITERALS) mlim = n - FAST_LASTLITERALS;

@@ -110,11 +110,10 @@ int b2_launch_fast(const FastArgs* a, b2_stream_t) {
   FastArgs args = *a;
   simt::launch(simt::Dim3(2), simt::Dim3(INDEX_WARPS * 32), INDEX_WARPS * FAST_TAB_BYTES, [&] { index_kernel(args); });
   const long long njobs = (long long)a->map.nfull * a->map.nsplits * a->groups_full + a->groups_left;
-  long long ctas = (njobs + PARSE_WARPS - 1) / PARSE_WARPS;
-  if (ctas > 3) ctas = 3;
+  long long ctas = njobs < 3 ? njobs : 3;
   args.queue_base = *a->queue_base_host;
-  *a->queue_base_host += (unsigned)njobs + (unsigned)ctas * PARSE_WARPS;
-  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(PARSE_WARPS * 32), 0, [&] { parse_kernel(args); });
+  *a->queue_base_host += (unsigned)njobs + (unsigned)ctas;
+  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(a->win_bytes / B2_FAST_SEG), (size_t)a->win_bytes + 32, [&] { parse_kernel(args); });
   return 0;
 }
 

@@ -68,7 +68,7 @@ typedef struct EncodeArgs {
 
 /* ---- segment-parallel LZ4 parse (dev_lz4fast.cuh) ---- */
 #define B2_FAST_SEG 256     /* bytes per segment (dev_lz4fast.cuh FAST_SEG) */
-#define B2_FAST_WIN_MAX (128 * 1024)   /* bytes of a stream that one parse CTA keeps in shared memory */
+#define B2_FAST_WIN_MAX (64 * 1024)   /* bytes of a stream that one parse CTA keeps in shared memory */
 typedef struct FastSeg {   /* one record per segment of FAST_SEG bytes */
   uint16_t nbytes;         /* bytes in the segment's slot (0: no match, the segment is all literals) */
   uint16_t l1;             /* literals in front of the segment's first match */

@@ -56,7 +56,7 @@ extern "C" int b2_device_prepare(void) {
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZSTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_WARPS * FAST_TAB_BYTES));
-  CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_FAST_WIN_MAX + 32));
+  CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_FAST_WIN_MAX + 64));
   CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
   return 0;
 }
@@ -226,7 +226,7 @@ extern "C" int b2_launch_fast(const FastArgs* a, b2_stream_t s) {
   {
     const long long njobs = (long long)a->map.nfull * a->map.nsplits * a->groups_full + a->groups_left;
     const int threads = a->win_bytes / B2_FAST_SEG;
-    const size_t smem = (size_t)a->win_bytes + 32;
+    const size_t smem = (size_t)a->win_bytes + 64;
     int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
     if (per_sm * threads > 2048) per_sm = 2048 / threads;
     if (per_sm < 1) per_sm = 1;
@@ -238,6 +238,12 @@ extern "C" int b2_launch_fast(const FastArgs* a, b2_stream_t s) {
     args.queue_base = *a->queue_base_host;
     *a->queue_base_host += (unsigned)njobs + (unsigned)ctas;      /* one ticket-drawing thread per CTA */
     parse_kernel<<<(unsigned)ctas, threads, smem, s->s>>>(args);
+    CK(cudaGetLastError());
+  }
+  {
+    const int ctas = (a->map.nstreams + FSCAN_WARPS - 1) / FSCAN_WARPS;
+    ProfScope ps(B2_K_SCAN, s->s);
+    fscan_kernel<<<ctas, FSCAN_WARPS * 32, 0, s->s>>>(*a);
     CK(cudaGetLastError());
   }
   return 0;

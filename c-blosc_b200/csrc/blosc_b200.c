@@ -660,6 +660,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
         fx.groups_full = (neblock + win - 1) / win; fx.groups_left = (leftover + win - 1) / win;
       }
       fx.depth = 3 * clevel + 1; fx.accel = ea.accel;
+      { const char* e = getenv("BLOSC_B200_FAST_DEPTH"); if (e && atoi(e) > 0) fx.depth = atoi(e); }   /* experiments */
       if (buf_ensure(&w->prev, 2 * (size_t)nb + 64)) break;
       if (buf_ensure(&w->segs, ((size_t)nfull * nsplits * fx.segs_full + fx.segs_left + 8) * sizeof(FastSeg))) break;
       if (buf_ensure_zeroed(w, &w->seg_done, (size_t)ea.map.nstreams * 4 + 64)) break;

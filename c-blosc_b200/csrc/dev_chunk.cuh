@@ -239,30 +239,28 @@ __global__ void __launch_bounds__(INDEX_WARPS * 32) index_kernel(FastArgs a) {
   }
 }
 
-/* One CTA per window of a stream (at most B2_FAST_WIN_MAX bytes, the whole stream for every split Blosc makes at
- * clevel <= 8): the window's bytes are staged in shared memory, then every THREAD parses one segment of FAST_SEG bytes.
+/* One CTA per window of a stream (at most B2_FAST_WIN_MAX bytes): the window's bytes are staged in shared memory, then every THREAD parses one segment of FAST_SEG bytes.
  * Candidate compares -- the random accesses of LZ matching -- hit shared memory; only the chain links (prev[]) and
  * candidates in front of the window come from L2. */
-__global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 1) parse_kernel(FastArgs a) {
+__global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 3) parse_kernel(FastArgs a) {
 #ifdef SIMT_EMU
   u8* smem = simt::g_dynsmem;
 #else
   extern __shared__ __align__(16) u8 smem[];
 #endif
   u32* sdata = (u32*)smem;
-  int* sjob = (int*)(smem + a.win_bytes + 16);
+  int* sjob = (int*)(smem + a.win_bytes + 48);
   const int tid = (int)threadIdx.x, lane = lane_id();
   const int nfs = a.map.nfull * a.map.nsplits;
   const int njobs = nfs * a.groups_full + a.groups_left;
   const int spw = a.win_bytes / FAST_SEG;         /* segments per window = threads per CTA */
-  int mine = 0;                                   /* streams completed (scanned) by this CTA's warp 0 */
   for (;;) {
     if (tid == 0) sjob[0] = (int)((unsigned)atomicAdd(a.queue, 1) - a.queue_base);
     __syncthreads();
     const int job = sjob[0];
     if (job >= njobs) break;
-    int idx, g, nwin, K;
-    if (job < a.groups_left) { idx = nfs; g = job; nwin = a.groups_left; K = a.segs_left; }
+    int idx, g, K;
+    if (job < a.groups_left) { idx = nfs; g = job; K = a.segs_left; }
     else {
       /* split-major, as next_stream: the byte-planes that turn out to be hard start first */
       const int j = job - a.groups_left;
@@ -270,7 +268,7 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 1) parse_kernel(Fa
       const int s = j / per_split, r = j - s * per_split;
       const int b = r / a.groups_full;
       g = r - b * a.groups_full;
-      idx = b * a.map.nsplits + s; nwin = a.groups_full; K = a.segs_full;
+      idx = b * a.map.nsplits + s; K = a.segs_full;
     }
     int block, len, split;
     long long off;
@@ -278,10 +276,22 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 1) parse_kernel(Fa
     FastSeg* segs = a.segs + (long long)idx * a.segs_full;
     FastView v = fast_view(a.in + off, len);
     const int wa = g * a.win_bytes, wb = wa + a.win_bytes < len ? wa + a.win_bytes : len;
-    const int i_lo = (wa + v.sal) >> 2;
-    int i_hi = (wb + v.sal + 3) >> 2;
-    if (i_hi > v.nwords) i_hi = v.nwords;
-    for (int i = i_lo + tid; i < i_hi; i += (int)blockDim.x) sdata[i - i_lo] = __ldg(v.w + i);
+    /* stage the 16-byte granules that overlap the window (they lie inside the buffer's allocation: device
+     * allocations start and end on coarser boundaries than that) */
+    int i_lo = (wa + v.sal) >> 2;
+    i_lo -= (int)(((uintptr_t)(v.w + i_lo) & 15u) >> 2);
+    const int i_hi = i_lo + ((((wb + v.sal + 3) >> 2) - i_lo + 3) & ~3);
+#ifdef SIMT_EMU
+    for (int i = i_lo + tid; i < i_hi; i += (int)blockDim.x) sdata[i - i_lo] = (i >= 0 && i < v.nwords) ? v.w[i] : 0u;
+#else
+    {
+      const uint4* g4 = (const uint4*)(v.w + i_lo);
+      uint4* s4 = (uint4*)sdata;
+      const int n4 = (i_hi - i_lo) >> 2;
+#pragma unroll 4
+      for (int i = tid; i < n4; i += (int)blockDim.x) s4[i] = __ldg(g4 + i);
+    }
+#endif
     __syncthreads();
     v.sm = sdata; v.sm_lo = i_lo; v.sm_hi = i_hi;
     const int k = g * spw + tid;
@@ -289,23 +299,29 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 1) parse_kernel(Fa
       const int sa = k * FAST_SEG, sb = sa + FAST_SEG < len ? sa + FAST_SEG : len;
       lz4f_parse_lane(v, len, a.prev + off, sa, sb, a.slots + off + sa, &segs[k], a.depth, a.accel);
     }
-    __threadfence();
-    __syncthreads();                               /* records are written; shared memory may be reused */
-    if (tid < 32) {
-      int last = 0;
-      if (lane == 0) last = atomicAdd(&a.seg_done[idx], 1) + 1 == nwin;
-      last = __shfl_sync(FULLMASK, last, 0);
-      if (last) {
-        __threadfence();
-        int ptail = 0;
-        int c = lz4f_stream_scan(segs, K, len, &ptail);
-        if (c >= len) c = len;                     /* blosc.c:705-714: incompressible split is stored raw */
-        if (lane == 0) { a.csizes[idx] = c; a.needs[idx] = c; a.ptail[idx] = ptail; a.seg_done[idx] = 0; }
-        mine++;
-      }
-    }
+    __syncthreads();                               /* shared memory may be reused */
   }
-  if (tid >= 32 || mine == 0) return;
+}
+
+/* One warp per stream: scan of its segment records (pending literals, continued matches, output offsets, compressed
+ * size); the warp that finishes the last stream runs the block scan, exactly as in encode_kernel. */
+#define FSCAN_WARPS 4
+__global__ void __launch_bounds__(FSCAN_WARPS * 32) fscan_kernel(FastArgs a) {
+  const int lane = lane_id();
+  const int nfs = a.map.nfull * a.map.nsplits;
+  int mine = 0;
+  for (int idx = (int)blockIdx.x * FSCAN_WARPS + (int)(threadIdx.x >> 5); idx < a.map.nstreams; idx += (int)gridDim.x * FSCAN_WARPS) {
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    int ptail = 0;
+    int c = lz4f_stream_scan(a.segs + (long long)idx * a.segs_full, idx < nfs ? a.segs_full : a.segs_left, len, &ptail);
+    if (c >= len) c = len;                         /* blosc.c:705-714: incompressible split is stored raw */
+    if (lane == 0) { a.csizes[idx] = c; a.needs[idx] = c; a.ptail[idx] = ptail; }
+    mine++;
+    __syncwarp();
+  }
+  if (mine == 0) return;
   __threadfence();
   int last = 0;
   if (lane == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;

@@ -79,27 +79,32 @@ DEV u32 fast_hash(u32 word, u32 b4) { return ((word * 2654435761u) ^ (b4 * 22468
 /* ---- index: prev[p] for every position of one stream, by one warp ----
  * Every step takes FAST_BATCH = 128 positions (4 consecutive ones per lane): hash, look the table up (state as of
  * the end of the previous step), then enter the 128 positions (atomicMax: the highest position wins, whatever the
- * order of the lanes).  The words of the next step are requested before this step's table work, so the only latency
- * on the step-to-step chain is the shared-memory round trip. */
-DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict__ prev, u32* tab) {
+ * order of the lanes).  A lane loads ONE aligned word per step -- its neighbours' words arrive by shuffle -- and the
+ * word of the next step is requested before this step's table work, so the only latency on the step-to-step
+ * chain is the shared-memory round trip.  Table entries are positions; "empty" is a position so far back that
+ * the distance test rejects it. */
+#define FAST_EMPTY (-(1 << 20))
+DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict__ prev, u32* tabmem) {
+  int* tab = (int*)tabmem;
   const int lane = lane_id();
-  for (int i = lane; i < (1 << FAST_HLOG); i += 32) tab[i] = 0;
+  for (int i = lane; i < (1 << FAST_HLOG); i += 32) tab[i] = FAST_EMPTY;
   __syncwarp();
   const FastView v = fast_view(s, n);
   const bool vec = (((uintptr_t)prev) & 7u) == 0;
   const u32 sh = (u32)v.sal * 8u;
-  const int wi = lane;                            /* lane's first word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane */
-  u32 n0 = fast_word(v, wi), n1 = fast_word(v, wi + 1), n2 = fast_word(v, wi + 2);
+  u32 nxt = fast_word(v, lane);                   /* lane's word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane */
   for (int base = 0; base < n; base += FAST_BATCH) {
     const int p0 = base + 4 * lane;
-    const u32 w0 = n0, w1 = n1, w2 = n2;
-    {
-      const int nx = ((base + FAST_BATCH) >> 2) + wi;
-      n0 = fast_word(v, nx); n1 = fast_word(v, nx + 1); n2 = fast_word(v, nx + 2);
-    }
+    const u32 w0 = nxt;
+    nxt = fast_word(v, ((base + FAST_BATCH) >> 2) + lane);
+    /* the two words behind the lane's own: the next lanes' words, or the first words of the next step */
+    const u32 d1 = __shfl_down_sync(FULLMASK, w0, 1), d2 = __shfl_down_sync(FULLMASK, w0, 2);
+    const u32 e0 = __shfl_sync(FULLMASK, nxt, 0), e1 = __shfl_sync(FULLMASK, nxt, 1);
+    const u32 w1 = lane < 31 ? d1 : e0, w2 = lane < 30 ? d2 : (lane == 30 ? e0 : e1);
     /* bytes p0 .. p0+7 */
     const u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
-    u32 h[4], c[4];
+    u32 h[4];
+    int c[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const u32 word = __funnelshift_r(v0, v1, 8u * j);
@@ -113,34 +118,34 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
         if (lane == m) {
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            c[j] = 0u;
-            if (p0 + j + 8 <= n) { c[j] = tab[h[j]]; tab[h[j]] = (u32)(p0 + j + 1); }
+            c[j] = FAST_EMPTY;
+            if (p0 + j + 8 <= n) { c[j] = tab[h[j]]; tab[h[j]] = p0 + j; }
           }
         }
         __syncwarp();
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++) c[j] = (full || p0 + j + 8 <= n) ? tab[h[j]] : 0u;
+      for (int j = 0; j < 4; j++) c[j] = (full || p0 + j + 8 <= n) ? tab[h[j]] : FAST_EMPTY;
       __syncwarp();
       /* a run (every position of the step hashes alike -- the zero planes of shuffled data) would make the
        * 128 atomics collide on one word: the last position enters it alone */
       const u32 hl = __shfl_sync(FULLMASK, h[3], 0);
       const bool same = h[0] == h[1] && h[1] == h[2] && h[2] == h[3] && h[3] == hl;
       if (full && __all_sync(FULLMASK, same)) {
-        if (lane == 31) tab[h[3]] = (u32)(p0 + 4);
+        if (lane == 31) tab[h[3]] = p0 + 3;
       } else {
 #pragma unroll
         for (int j = 0; j < 4; j++)
-          if ((full || p0 + j + 8 <= n) && (j == 3 || h[j] != h[j + 1])) atomicMax(&tab[h[j]], (u32)(p0 + j + 1));
+          if ((full || p0 + j + 8 <= n) && (j == 3 || h[j] != h[j + 1])) atomicMax(&tab[h[j]], p0 + j);
       }
       __syncwarp();
     }
     u32 d[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const u32 delta = (u32)(p0 + j + 1) - c[j];           /* c = position + 1 */
-      d[j] = (c[j] != 0u && delta <= 65535u) ? delta : 0u;
+      const u32 delta = (u32)(p0 + j - c[j]);
+      d[j] = delta <= 65535u ? delta : 0u;
     }
     if (p0 + 4 <= n && vec) *(uint2*)(prev + p0) = make_uint2(d[0] | (d[1] << 16), d[2] | (d[3] << 16));
     else {
@@ -150,26 +155,48 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
   }
 }
 
-/* number of equal bytes of s[p..] and s[q..] (q < p), at most `lim` */
+/* number of equal bytes of s[p..] and s[q..] (q < p), at most `lim`: one new aligned word per side and 4 bytes */
 DEV int fast_count(const FastView& v, int p, int q, int lim) {
+  if (lim <= 0) return 0;
+  int pi = (p + v.sal) >> 2, qi = (q + v.sal) >> 2;
+  const u32 psh = (u32)((p + v.sal) & 3) * 8u, qsh = (u32)((q + v.sal) & 3) * 8u;
   int c = 0;
-  while (c + 4 <= lim) {
-    const u32 x = fast_ld32(v, p + c) ^ fast_ld32(v, q + c);
-    if (x) return c + ((__ffs((int)x) - 1) >> 3);
-    c += 4;
+  if (qi >= v.sm_lo && pi + (lim >> 2) + 2 < v.sm_hi) {        /* both sides inside the shared-memory window */
+    const u32* ps = v.sm + (pi - v.sm_lo);
+    const u32* qs = v.sm + (qi - v.sm_lo);
+    u32 pl = ps[0], ql = qs[0];
+    for (;;) {
+      const u32 ph = *++ps, qh = *++qs;
+      const u32 x = __funnelshift_r(pl, ph, psh) ^ __funnelshift_r(ql, qh, qsh);
+      if (x) { c += (__ffs((int)x) - 1) >> 3; break; }
+      c += 4;
+      if (c >= lim) break;
+      pl = ph; ql = qh;
+    }
+  } else {
+    u32 pl = fast_word(v, pi), ql = fast_word(v, qi);
+    for (;;) {
+      const u32 ph = fast_word(v, ++pi), qh = fast_word(v, ++qi);
+      const u32 x = __funnelshift_r(pl, ph, psh) ^ __funnelshift_r(ql, qh, qsh);
+      if (x) { c += (__ffs((int)x) - 1) >> 3; break; }
+      c += 4;
+      if (c >= lim) break;
+      pl = ph; ql = qh;
+    }
   }
-  while (c < lim && fast_ld8(v, p + c) == fast_ld8(v, q + c)) c++;
-  return c;
+  return c < lim ? c : lim;
 }
 
 DEV int fast_lit_ext(int lit) { return lit >= 15 ? 1 + (lit - 15) / 255 : 0; }
 
 /* Longest match for position ip among: the offset `rep`, the offsets 1..4, and up to `de` candidates of the hash
  * chain.  Returns its length (0: none) and *off. */
-DEV int lz4f_search(const FastView& v, const u16* __restrict__ prev, const int ip, const int mlim, const int rep, const int de, int* off) {
+DEV int lz4f_search(const FastView& v, const u16* __restrict__ prev, const int ip, const int mlim, const int rep, const int rep_len,
+                    const int de, int* off) {
   const u32 wip = fast_ld32(v, ip);
   int best = 0, boff = 0, q = ip;
-  if (rep && fast_ld32(v, ip - rep) == wip) {
+  if (rep_len) { best = rep_len; boff = rep; }            /* already counted by the caller */
+  else if (rep && fast_ld32(v, ip - rep) == wip) {
     best = 4 + fast_count(v, ip + 4, ip - rep + 4, mlim - (ip + 4));
     boff = rep;
   }
@@ -224,7 +251,7 @@ DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__
    * data: the match that a glitch ended resumes right behind it).  At the start of a segment it is whichever chain
    * candidate of the byte in FRONT of the segment continues best into it -- normally the offset the previous
    * segment's lane ends with, so that a match which covers this whole segment can simply be continued. */
-  int rep = 0;
+  int rep = 0, pre = 0;
   if (a > 0 && a <= mfl) {
     const u32 wa = fast_ld32(v, a);
     int q = a - 1, bl = 0;
@@ -240,17 +267,18 @@ DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__
         if (a + len >= mlim) break;
       }
     }
+    pre = bl;
   }
   while (ip <= mfl) {
     int de = depth >> ((miss >> 3) < 5 ? (miss >> 3) : 5);   /* a run of misses (incompressible data) shortens the chain walk */
     if (de < 2) de = 2;
     int boff = 0;
-    int best = lz4f_search(v, prev, ip, mlim, rep, de, &boff);
+    int best = lz4f_search(v, prev, ip, mlim, rep, ip == a ? pre : 0, de, &boff);
     if (best >= 4 && best < FAST_LAZY && ip + 1 <= mfl) {
       /* lazy evaluation (as LZ4HC / zlib): a short match is given up for a literal when the next position
        * starts a longer one */
       int boff2 = 0;
-      const int best2 = lz4f_search(v, prev, ip + 1, mlim, rep, de, &boff2);
+      const int best2 = lz4f_search(v, prev, ip + 1, mlim, rep, 0, de, &boff2);
       if (best2 > best + 1) { ip++; best = best2; boff = boff2; }
     }
     const int lit = ip - anchor;

@@ -106,14 +106,15 @@ int b2_launch_encode(const EncodeArgs* a, b2_stream_t) {
 
 int b2_launch_fast(const FastArgs* a, b2_stream_t) {
   if (a->map.nstreams <= 0) return 0;
-  g_launches += 2;
+  g_launches += 3;
   FastArgs args = *a;
   simt::launch(simt::Dim3(2), simt::Dim3(INDEX_WARPS * 32), INDEX_WARPS * FAST_TAB_BYTES, [&] { index_kernel(args); });
   const long long njobs = (long long)a->map.nfull * a->map.nsplits * a->groups_full + a->groups_left;
   long long ctas = njobs < 3 ? njobs : 3;
   args.queue_base = *a->queue_base_host;
   *a->queue_base_host += (unsigned)njobs + (unsigned)ctas;
-  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(a->win_bytes / B2_FAST_SEG), (size_t)a->win_bytes + 32, [&] { parse_kernel(args); });
+  simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(a->win_bytes / B2_FAST_SEG), (size_t)a->win_bytes + 64, [&] { parse_kernel(args); });
+  simt::launch(simt::Dim3(2), simt::Dim3(FSCAN_WARPS * 32), 0, [&] { fscan_kernel(args); });
   return 0;
 }
 

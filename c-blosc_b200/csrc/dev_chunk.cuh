@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 3) parse_kernel(Fa
 #endif
     __syncthreads();
     v.sm = sdata; v.sm_lo = i_lo; v.sm_hi = i_hi;
+    v.lo_pos = wa; v.bias = v.sal - 4 * i_lo;      /* position p is byte p + sal - 4 i_lo of the staged words */
     const int k = g * spw + tid;
     if (k < K && tid < spw) {
       const int sa = k * FAST_SEG, sb = sa + FAST_SEG < len ? sa + FAST_SEG : len;

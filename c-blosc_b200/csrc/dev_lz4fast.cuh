@@ -38,6 +38,9 @@
 #endif
 #define FAST_LAZY 0                  /* matches shorter than this are checked against the next position's match */
 #define FAST_NICE 4096                  /* a match this long is taken without walking the chain */
+#ifndef HMASK
+#define HMASK 0xffffu
+#endif
 #define FAST_MFLIMIT 12               /* lz4.c:239-243: the last match starts >= 12 bytes before the end ... */
 #define FAST_LASTLITERALS 5           /* ... and the last 5 bytes are literals */
 
@@ -48,13 +51,15 @@ struct FastView {
   int nwords;        /* words that overlap the stream */
   const u32* sm;     /* words [sm_lo, sm_hi) of the stream are also in shared memory, at sm[i - sm_lo] */
   int sm_lo, sm_hi;
+  int lo_pos;        /* positions >= lo_pos (and below the end of the window) can be read from shared memory ... */
+  int bias;          /* ... at byte p + bias of `sm` */
 };
 DEV FastView fast_view(const u8* s, int n) {
   FastView v;
   v.sal = (int)((uintptr_t)s & 3u);
   v.w = (const u32*)(s - v.sal);
   v.nwords = (n + v.sal + 3) >> 2;
-  v.sm = nullptr; v.sm_lo = 0; v.sm_hi = 0;
+  v.sm = nullptr; v.sm_lo = 0; v.sm_hi = 0; v.lo_pos = 0x7fffffff; v.bias = 0;
   return v;
 }
 DEV u32 fast_word(const FastView& v, int i) {
@@ -63,6 +68,11 @@ DEV u32 fast_word(const FastView& v, int i) {
 }
 /* 4 bytes at position p (p >= 0); bytes past the end of the stream read as zero */
 DEV u32 fast_ld32(const FastView& v, int p) {
+  if (p >= v.lo_pos) {                             /* the common case: inside the window */
+    const u32 x = (u32)(p + v.bias);
+    const u32* w = v.sm + (x >> 2);
+    return __funnelshift_r(w[0], w[1], (x & 3u) * 8u);
+  }
   const int q = p + v.sal;
   const u32 lo = fast_word(v, q >> 2);
   const u32 sh = (u32)(q & 3) * 8u;
@@ -92,23 +102,31 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
   const FastView v = fast_view(s, n);
   const bool vec = (((uintptr_t)prev) & 7u) == 0;
   const u32 sh = (u32)v.sal * 8u;
-  u32 nxt = fast_word(v, lane);                   /* lane's word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane */
+  /* lane's word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane.  The step uses its own words and two words
+   * of the next step: both were requested at least a step ago, and one lane pulls the line of eight steps ahead
+   * into L1, so that no step waits for DRAM. */
+  u32 cur = fast_word(v, lane), nxt = fast_word(v, (FAST_BATCH >> 2) + lane);
   for (int base = 0; base < n; base += FAST_BATCH) {
     const int p0 = base + 4 * lane;
-    const u32 w0 = nxt;
-    nxt = fast_word(v, ((base + FAST_BATCH) >> 2) + lane);
+    const u32 w0 = cur;
+    cur = nxt;
+    nxt = fast_word(v, ((base + 2 * FAST_BATCH) >> 2) + lane);
+#ifndef SIMT_EMU
+    if (lane == 0 && base + 10 * FAST_BATCH < n) asm volatile("prefetch.global.L1 [%0];" :: "l"(s + base + 8 * FAST_BATCH));
+#endif
     /* the two words behind the lane's own: the next lanes' words, or the first words of the next step */
     const u32 d1 = __shfl_down_sync(FULLMASK, w0, 1), d2 = __shfl_down_sync(FULLMASK, w0, 2);
-    const u32 e0 = __shfl_sync(FULLMASK, nxt, 0), e1 = __shfl_sync(FULLMASK, nxt, 1);
+    const u32 e0 = __shfl_sync(FULLMASK, cur, 0), e1 = __shfl_sync(FULLMASK, cur, 1);
     const u32 w1 = lane < 31 ? d1 : e0, w2 = lane < 30 ? d2 : (lane == 30 ? e0 : e1);
     /* bytes p0 .. p0+7 */
     const u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
+    const u32 w3d = __shfl_down_sync(FULLMASK, w0, 3); const u32 w3e = __shfl_sync(FULLMASK, cur, (lane + 3) & 31); const u32 w2x = __funnelshift_r(w2, lane < 29 ? w3d : w3e, sh);
     u32 h[4];
     int c[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const u32 word = __funnelshift_r(v0, v1, 8u * j);
-      h[j] = fast_hash(word, (v1 >> (8u * j)) & 0xffu);
+      h[j] = fast_hash(word, HMASK & (j == 0 ? v1 : __funnelshift_r(v1, w2x, 8u * j)));
     }
     const bool full = base + FAST_BATCH + 8 <= n;  /* every position of the step has its 8 bytes inside the stream */
     if (base == 0) {
@@ -158,12 +176,12 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
 /* number of equal bytes of s[p..] and s[q..] (q < p), at most `lim`: one new aligned word per side and 4 bytes */
 DEV int fast_count(const FastView& v, int p, int q, int lim) {
   if (lim <= 0) return 0;
-  int pi = (p + v.sal) >> 2, qi = (q + v.sal) >> 2;
-  const u32 psh = (u32)((p + v.sal) & 3) * 8u, qsh = (u32)((q + v.sal) & 3) * 8u;
   int c = 0;
-  if (qi >= v.sm_lo && pi + (lim >> 2) + 2 < v.sm_hi) {        /* both sides inside the shared-memory window */
-    const u32* ps = v.sm + (pi - v.sm_lo);
-    const u32* qs = v.sm + (qi - v.sm_lo);
+  if (q >= v.lo_pos) {                                          /* both sides inside the shared-memory window */
+    const u32 px = (u32)(p + v.bias), qx = (u32)(q + v.bias);
+    const u32 psh = (px & 3u) * 8u, qsh = (qx & 3u) * 8u;
+    const u32* ps = v.sm + (px >> 2);
+    const u32* qs = v.sm + (qx >> 2);
     u32 pl = ps[0], ql = qs[0];
     for (;;) {
       const u32 ph = *++ps, qh = *++qs;
@@ -174,6 +192,8 @@ DEV int fast_count(const FastView& v, int p, int q, int lim) {
       pl = ph; ql = qh;
     }
   } else {
+    int pi = (p + v.sal) >> 2, qi = (q + v.sal) >> 2;
+    const u32 psh = (u32)((p + v.sal) & 3) * 8u, qsh = (u32)((q + v.sal) & 3) * 8u;
     u32 pl = fast_word(v, pi), ql = fast_word(v, qi);
     for (;;) {
       const u32 ph = fast_word(v, ++pi), qh = fast_word(v, ++qi);
@@ -201,15 +221,22 @@ DEV int lz4f_search(const FastView& v, const u16* __restrict__ prev, const int i
     boff = rep;
   }
   if (ip + best < mlim && best < FAST_NICE) {
+    u32 wend = best >= 4 ? fast_ld32(v, ip + best - 3) : 0u;   /* bytes [best-3, best] of the position: the first one a longer match adds */
     for (int d = 0; d < de; d++) {
       const int dl = (int)prev[q];
       if (dl == 0) break;
       q -= dl;
       if (ip - q > 65535) break;
+      /* a candidate can only win if it also matches where the best match so far ends (the LZ4HC test,
+       * lz4hc.c LZ4HC_InsertAndGetWiderMatch): most candidates are turned down by this one compare */
+      if (best >= 4 && fast_ld32(v, q + best - 3) != wend) continue;
       if (fast_ld32(v, q) == wip) {
         const int len = 4 + fast_count(v, ip + 4, q + 4, mlim - (ip + 4));
-        if (len > best) { best = len; boff = ip - q; }
-        if (ip + len >= mlim) break;             /* cannot get longer */
+        if (len > best) {
+          best = len; boff = ip - q;
+          if (ip + len >= mlim) break;           /* cannot get longer */
+          wend = fast_ld32(v, ip + best - 3);
+        }
       }
     }
   }

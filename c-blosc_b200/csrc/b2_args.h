@@ -57,6 +57,7 @@ typedef struct EncodeArgs {
   int codec, clevel, accel, split_flag;
   int table_bytes;       /* shared-memory bytes per warp */
   int num_sms;           /* filled in by the backend (team kernel: spreads the walker warps over the SM sub-partitions) */
+  int many;              /* other chunks are in flight on this device (frames): streams per SM matter more than latency */
   int* queue;            /* work counter: warps pull stream numbers from it.  It only ever counts up: a launch
                           * adds exactly nstreams + (warps launched) tickets, the backend keeps the running base */
   unsigned queue_base;   /* first ticket of this launch (filled in by the backend) */

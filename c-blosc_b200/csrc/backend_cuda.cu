@@ -49,6 +49,8 @@ extern "C" int b2_device_prepare(void) {
     CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     g_sms[dev] = n;
   }
+  /* (no cudaFuncAttributePreferredSharedMemoryCarveout: measured, the codec kernels are faster with the driver's
+   * default split -- fewer resident CTAs but more L1 -- than with the largest shared-memory carve-out) */
   CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(encode_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TEAM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_LZ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
@@ -178,11 +180,17 @@ extern "C" int b2_launch_filter(const FilterArgs* a, b2_stream_t s) {
   return 0;
 }
 
-/* LZ4 with the plain 16 KiB table runs in team mode (BLOSC_B200_LZ4_TEAM=0 falls back to one warp per stream) */
+/* LZ4 with the plain 16 KiB table can run in team mode (one CTA of four warps per stream).  It shortens the
+ * critical path of a hard stream but keeps fewer streams in flight, so it pays when most streams of a block are
+ * cheap and one is hard -- measured on the bench.c planes: +20 % at typesize 4 (one hard byte-plane of four),
+ * -50 % at typesize 2 (both planes hard), -25 % at typesize 8 / 16.  Default: blocks of four splits when the
+ * chunk has the device to itself (a frame keeps several chunks in flight: streams per SM win there);
+ * BLOSC_B200_LZ4_TEAM=0 / 1 forces it off / on. */
 static int team_wanted(const EncodeArgs* a) {
-  static int env = -1;
-  if (env < 0) { const char* e = getenv("BLOSC_B200_LZ4_TEAM"); env = (e && *e) ? atoi(e) != 0 : 1; }
-  return env && a->codec == B2_CODEC_LZ4 && a->table_bytes == LZ4_TABLE_BYTES;
+  static int env = -2;
+  if (env == -2) { const char* e = getenv("BLOSC_B200_LZ4_TEAM"); env = (e && *e) ? (atoi(e) != 0) : -1; }
+  if (a->codec != B2_CODEC_LZ4 || a->table_bytes != LZ4_TABLE_BYTES) return 0;
+  return env >= 0 ? env : (a->map.nsplits == 4 && !a->many);
 }
 
 extern "C" int b2_launch_encode(const EncodeArgs* a, b2_stream_t s) {

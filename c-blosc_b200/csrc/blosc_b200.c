@@ -627,6 +627,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
     ea.codec = compcode == BLOSC_LZ4 ? B2_CODEC_LZ4 : B2_CODEC_BLOSCLZ;
     ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
     ea.split_flag = !dont_split;
+    ea.many = pl ? pl->many : 0;
     ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
     /* BloscLZ at clevel >= 3: 17-bit packed table (34 KiB instead of 64 KiB) when every stream is <= 128 KiB */
     if (ea.codec == B2_CODEC_BLOSCLZ && clevel >= 3 && bs / nsplits <= 131072 && leftover <= 131072) ea.table_bytes = 32768 + 2048;

@@ -187,6 +187,15 @@ static void ws_reset_counters(b2_ws* w) {
   w->queue_base = 0;
 }
 
+/* calls in flight on `dev` right now (the caller's own included) */
+static int ws_busy(int dev) {
+  int i, n = 0;
+  pthread_mutex_lock(&g_ws_mutex);
+  for (i = 0; i < B2_MAX_WS; i++) if (g_ws[i].in_use && g_ws[i].ready && g_ws[i].dev == dev) n++;
+  pthread_mutex_unlock(&g_ws_mutex);
+  return n;
+}
+
 static void ws_release(b2_ws* w) {
   pthread_mutex_lock(&g_ws_mutex);
   w->in_use = 0;
@@ -627,7 +636,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
     ea.codec = compcode == BLOSC_LZ4 ? B2_CODEC_LZ4 : B2_CODEC_BLOSCLZ;
     ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
     ea.split_flag = !dont_split;
-    ea.many = pl ? pl->many : 0;
+    ea.many = (pl && pl->many) || ws_busy(w->dev) > 1;      /* a frame, or other _ctx calls running on this device */
     ea.table_bytes = ea.codec == B2_CODEC_LZ4 ? 16384 : (4 << (clevel == 1 ? 12 : (clevel == 2 ? 13 : 14)));
     /* BloscLZ at clevel >= 3: 17-bit packed table (34 KiB instead of 64 KiB) when every stream is <= 128 KiB */
     if (ea.codec == B2_CODEC_BLOSCLZ && clevel >= 3 && bs / nsplits <= 131072 && leftover <= 131072) ea.table_bytes = 32768 + 2048;

@@ -169,9 +169,11 @@ extern "C" int b2_launch_filter(const FilterArgs* a, b2_stream_t s) {
   const bool bit = a->mode >= FILT_BITSHUFFLE;
   const bool inverse = a->mode == FILT_UNSHUFFLE || a->mode == FILT_BITUNSHUFFLE;
   const long long nblocks = (a->nbytes + a->blocksize - 1) / a->blocksize;
-  const long long ipb = (a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1;
+  const long long ipb = ((a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1 + FILT_GROUP - 1) / FILT_GROUP;
   long long ctas = (nblocks * ipb + FILT_WARPS - 1) / FILT_WARPS;
-  const long long cap = (long long)num_sms() * 8;
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("BLOSC_B200_FILT_CTAS"); per_sm = (e && atoi(e) > 0) ? atoi(e) : 8; }
+  const long long cap = (long long)num_sms() * per_sm;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   ProfScope ps(inverse ? B2_K_UNFILTER : B2_K_FILTER, s->s);

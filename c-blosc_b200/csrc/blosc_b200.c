@@ -919,8 +919,28 @@ static int getitem_impl(const void* src, int start, int nitems, void* dest, long
     const int count = (int)(last - first + 1);
     if (src_dev) d_chunk = (const uint8_t*)src;
     else {
+      /* only what the decoder will read crosses PCIe: the header with bstarts[], and the bytes of the blocks that
+       * overlap the request -- from the lowest of their bstarts to the next bstart above the highest (blosc.c:1655-1668
+       * decodes just those blocks; the kernel bounds-checks every offset against cbytes as blosc_d does) */
+      const uint8_t* hs = (const uint8_t*)src;
+      const size_t index_end = 16 + 4 * (size_t)h.nblocks;
+      size_t lo = (size_t)h.cbytes, hi = 0, cut = (size_t)h.cbytes;
+      long long b;
+      int bad = 0;
       if (buf_ensure(&w->in, (size_t)h.cbytes + 64)) break;
-      if (h2d_any(w, w->in.p, src, (size_t)h.cbytes)) break;
+      for (b = first; b <= last; b++) {
+        const int32_t bs_b = rd_i32(hs + 16 + 4 * b);
+        if (bs_b < (int32_t)index_end || bs_b > h.cbytes) { bad = 1; break; }
+        if ((size_t)bs_b < lo) lo = (size_t)bs_b;
+        if ((size_t)bs_b > hi) hi = (size_t)bs_b;
+      }
+      if (bad) { result = -1; break; }                                     /* blosc_d would refuse this offset (blosc.c:761) */
+      for (b = 0; b < h.nblocks; b++) {                                    /* where the last needed block ends */
+        const int32_t bs_b = rd_i32(hs + 16 + 4 * b);
+        if ((size_t)bs_b > hi && (size_t)bs_b < cut) cut = (size_t)bs_b;
+      }
+      if (h2d_any(w, w->in.p, hs, index_end)) break;
+      if (h2d_any(w, (uint8_t*)w->in.p + lo, hs + lo, cut - lo)) break;
       d_chunk = (const uint8_t*)w->in.p;
     }
     if (buf_ensure(&w->out, (size_t)count * (size_t)h.blocksize + 64)) break;

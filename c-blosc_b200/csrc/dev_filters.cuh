@@ -94,7 +94,7 @@ DEV void planes_to_store4(u8* __restrict__ p, const u32 (&pl)[TS]) {
 template <int TS>
 DEV void tile_shuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e0) {
   const int lane = lane_id();
-#pragma unroll 2
+#pragma unroll 4
   for (int q = 0; q < FILT_TILE / 128; q++) {
     const int e = e0 + q * 128 + 4 * lane;
     u32 pl[TS];
@@ -107,7 +107,7 @@ DEV void tile_shuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e
 template <int TS>
 DEV void tile_unshuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e0) {
   const int lane = lane_id();
-#pragma unroll 2
+#pragma unroll 4
   for (int q = 0; q < FILT_TILE / 128; q++) {
     const int e = e0 + q * 128 + 4 * lane;
     u32 pl[TS];
@@ -263,6 +263,8 @@ DEV void filter_item(int mode, const u8* __restrict__ s, u8* __restrict__ d, int
 }
 
 #define FILT_WARPS 4
+#define FILT_GROUP 4              /* tiles per work item: the index arithmetic of an item (and the bubble before its first
+                                   * loads) is paid once per 4 tiles */
 /* dynamic shared memory: FILT_WARPS * 16 * FILT_TILE bytes for the bit modes (0 otherwise) */
 __global__ void __launch_bounds__(FILT_WARPS * 32) filter_kernel(FilterArgs a) {
 #ifdef SIMT_EMU
@@ -274,14 +276,17 @@ __global__ void __launch_bounds__(FILT_WARPS * 32) filter_kernel(FilterArgs a) {
   u8* sm = smem + (size_t)warp * (16 * FILT_TILE);
   const long long nblocks = (a.nbytes + a.blocksize - 1) / a.blocksize;
   const int tiles_per_block = (a.blocksize / a.typesize + FILT_TILE - 1) / FILT_TILE;
-  const int ipb = tiles_per_block + 1;            /* + tail item */
-  const long long nitems = nblocks * ipb;
+  const int gpb = (tiles_per_block + 1 + FILT_GROUP - 1) / FILT_GROUP;   /* groups per block; the tail item is tile number tiles_per_block */
+  const long long nitems = nblocks * gpb;
   for (long long it = (long long)blockIdx.x * FILT_WARPS + warp; it < nitems; it += (long long)gridDim.x * FILT_WARPS) {
-    const long long b = it / ipb;
-    const int t = (int)(it - b * ipb);
+    long long b;
+    int g;
+    if (nitems < 0x7fffffffll) { const unsigned ui = (unsigned)it; b = ui / (unsigned)gpb; g = (int)(ui - (unsigned)b * (unsigned)gpb); }
+    else { b = it / gpb; g = (int)(it - b * gpb); }
     const long long b0 = b * a.blocksize;
     const long long rem = a.nbytes - b0;
     const int bsize = rem < a.blocksize ? (int)rem : a.blocksize;
-    filter_item(a.mode, a.src + b0, a.dst + b0, a.typesize, bsize, t, tiles_per_block, sm);
+    for (int t = g * FILT_GROUP; t < (g + 1) * FILT_GROUP && t <= tiles_per_block; t++)
+      filter_item(a.mode, a.src + b0, a.dst + b0, a.typesize, bsize, t, tiles_per_block, sm);
   }
 }

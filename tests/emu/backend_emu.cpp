@@ -63,7 +63,7 @@ long long b2_launch_count(void) { return g_launches; }
 int b2_launch_filter(const FilterArgs* a, b2_stream_t) {
   const bool bit = a->mode >= FILT_BITSHUFFLE;
   const long long nblocks = (a->nbytes + a->blocksize - 1) / a->blocksize;
-  const long long ipb = (a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1;
+  const long long ipb = ((a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1 + FILT_GROUP - 1) / FILT_GROUP;
   long long ctas = (nblocks * ipb + FILT_WARPS - 1) / FILT_WARPS;
   if (ctas > 7) ctas = 7;          /* small odd grid: exercises the grid-stride loop */
   if (ctas < 1) ctas = 1;

@@ -385,7 +385,7 @@ def measure_traffic(workload):
     workload: a separate short `ncu` run of scripts/kbench.py (counters only -- nothing timed under the profiler)."""
     comp_name, shuf, ts, clevel, nbytes = WORKLOADS[workload]
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
-           "regex:encode_kernel|decode_kernel", "-s", "6", "-c", "2", "--csv", sys.executable,
+           "regex:encode_kernel|encode_team_kernel|decode_kernel", "-s", "6", "-c", "2", "--csv", sys.executable,
            os.path.join(ROOT, "scripts", "kbench.py"), "ncu", f"{comp_name}:{shuf}:{ts}"]
     try:
         env = dict(os.environ, KBENCH_STEPS="1")
@@ -396,7 +396,7 @@ def measure_traffic(workload):
         rows = list(csv.DictReader(io.StringIO(out[start:])))
         acc = {}
         for r in rows:
-            kname = "encode" if "encode_kernel" in r.get("Kernel Name", "") else "decode"
+            kname = "encode" if "encode" in r.get("Kernel Name", "") else "decode"
             v = float(r["Metric Value"].replace(",", ""))
             u = r.get("Metric Unit", "byte").lower()
             v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)

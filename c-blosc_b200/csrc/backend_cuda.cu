@@ -59,7 +59,10 @@ extern "C" int b2_device_prepare(void) {
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZSTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INDEX_WARPS * FAST_TAB_BYTES));
   CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_FAST_WIN_MAX + 64));
-  CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
+  CK(cudaFuncSetAttribute(filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
+  CK(cudaFuncSetAttribute(filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
+  CK(cudaFuncSetAttribute(filter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
+  CK(cudaFuncSetAttribute(filter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FILT_WARPS * 16 * FILT_TILE));
   return 0;
 }
 
@@ -169,15 +172,19 @@ extern "C" int b2_launch_filter(const FilterArgs* a, b2_stream_t s) {
   const bool bit = a->mode >= FILT_BITSHUFFLE;
   const bool inverse = a->mode == FILT_UNSHUFFLE || a->mode == FILT_BITUNSHUFFLE;
   const long long nblocks = (a->nbytes + a->blocksize - 1) / a->blocksize;
-  const long long ipb = ((a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1 + FILT_GROUP - 1) / FILT_GROUP;
+  const long long ipb = (a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1;
   long long ctas = (nblocks * ipb + FILT_WARPS - 1) / FILT_WARPS;
-  static int per_sm = 0;
-  if (!per_sm) { const char* e = getenv("BLOSC_B200_FILT_CTAS"); per_sm = (e && atoi(e) > 0) ? atoi(e) : 8; }
+  /* one kernel instantiation per common typesize; the grid is exactly what is resident (a grid-stride loop with a
+   * partial second wave ends with most SMs idle) */
+  void (*kern)(FilterArgs) = a->typesize == 2 ? filter_kernel<2> : a->typesize == 4 ? filter_kernel<4> : a->typesize == 8 ? filter_kernel<8> : filter_kernel<0>;
+  const size_t smem = bit ? FILT_WARPS * 16 * FILT_TILE : 0;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FILT_WARPS * 32, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
   const long long cap = (long long)num_sms() * per_sm;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   ProfScope ps(inverse ? B2_K_UNFILTER : B2_K_FILTER, s->s);
-  filter_kernel<<<(unsigned)ctas, FILT_WARPS * 32, bit ? FILT_WARPS * 16 * FILT_TILE : 0, s->s>>>(*a);
+  kern<<<(unsigned)ctas, FILT_WARPS * 32, smem, s->s>>>(*a);
   CK(cudaGetLastError());
   return 0;
 }

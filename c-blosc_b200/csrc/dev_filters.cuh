@@ -230,7 +230,9 @@ DEV void tile_fast(int mode, const u8* __restrict__ s, u8* __restrict__ d, int N
 }
 
 /* One warp work item: tile `t` of block whose (already offset) bases are s/d.
- * t == ntiles_full_block is the "tail" item (bytes past N*ts). */
+ * t == ntiles_full_block is the "tail" item (bytes past N*ts).  TSK > 0: the kernel was instantiated for this
+ * typesize (the register count of the typesize-16 transposes must not cap the occupancy of the typesize-4 ones). */
+template <int TSK>
 DEV void filter_item(int mode, const u8* __restrict__ s, u8* __restrict__ d, int ts, int bsize, int t,
                      int tail_item, u8* sm) {
   const int N = bsize / ts;
@@ -250,6 +252,7 @@ DEV void filter_item(int mode, const u8* __restrict__ s, u8* __restrict__ d, int
   }
   const bool aligned = ((((uintptr_t)s) | ((uintptr_t)d)) & 15u) == 0 && (N & 31) == 0;
   if (aligned && e1 - e0 == FILT_TILE) {
+    if (TSK > 0) { tile_fast<TSK == 0 ? 1 : TSK>(mode, s, d, N, e0, sm); return; }
     switch (ts) {
       case 1: if (bitmode) { tile_fast<1>(mode, s, d, N, e0, sm); return; } break;
       case 2: tile_fast<2>(mode, s, d, N, e0, sm); return;
@@ -263,10 +266,9 @@ DEV void filter_item(int mode, const u8* __restrict__ s, u8* __restrict__ d, int
 }
 
 #define FILT_WARPS 4
-#define FILT_GROUP 4              /* tiles per work item: the index arithmetic of an item (and the bubble before its first
-                                   * loads) is paid once per 4 tiles */
 /* dynamic shared memory: FILT_WARPS * 16 * FILT_TILE bytes for the bit modes (0 otherwise) */
-__global__ void __launch_bounds__(FILT_WARPS * 32) filter_kernel(FilterArgs a) {
+template <int TSK>
+__global__ void __launch_bounds__(FILT_WARPS * 32, TSK == 0 ? 4 : 8) filter_kernel(FilterArgs a) {
 #ifdef SIMT_EMU
   u8* smem = simt::g_dynsmem;
 #else
@@ -276,17 +278,16 @@ __global__ void __launch_bounds__(FILT_WARPS * 32) filter_kernel(FilterArgs a) {
   u8* sm = smem + (size_t)warp * (16 * FILT_TILE);
   const long long nblocks = (a.nbytes + a.blocksize - 1) / a.blocksize;
   const int tiles_per_block = (a.blocksize / a.typesize + FILT_TILE - 1) / FILT_TILE;
-  const int gpb = (tiles_per_block + 1 + FILT_GROUP - 1) / FILT_GROUP;   /* groups per block; the tail item is tile number tiles_per_block */
-  const long long nitems = nblocks * gpb;
+  const int ipb = tiles_per_block + 1;            /* + tail item */
+  const long long nitems = nblocks * ipb;
   for (long long it = (long long)blockIdx.x * FILT_WARPS + warp; it < nitems; it += (long long)gridDim.x * FILT_WARPS) {
     long long b;
-    int g;
-    if (nitems < 0x7fffffffll) { const unsigned ui = (unsigned)it; b = ui / (unsigned)gpb; g = (int)(ui - (unsigned)b * (unsigned)gpb); }
-    else { b = it / gpb; g = (int)(it - b * gpb); }
+    int t;
+    if (nitems < 0x7fffffffll) { const unsigned ui = (unsigned)it; b = ui / (unsigned)ipb; t = (int)(ui - (unsigned)b * (unsigned)ipb); }
+    else { b = it / ipb; t = (int)(it - b * ipb); }
     const long long b0 = b * a.blocksize;
     const long long rem = a.nbytes - b0;
     const int bsize = rem < a.blocksize ? (int)rem : a.blocksize;
-    for (int t = g * FILT_GROUP; t < (g + 1) * FILT_GROUP && t <= tiles_per_block; t++)
-      filter_item(a.mode, a.src + b0, a.dst + b0, a.typesize, bsize, t, tiles_per_block, sm);
+    filter_item<TSK>(a.mode, a.src + b0, a.dst + b0, a.typesize, bsize, t, tiles_per_block, sm);
   }
 }

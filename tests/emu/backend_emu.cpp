@@ -63,14 +63,14 @@ long long b2_launch_count(void) { return g_launches; }
 int b2_launch_filter(const FilterArgs* a, b2_stream_t) {
   const bool bit = a->mode >= FILT_BITSHUFFLE;
   const long long nblocks = (a->nbytes + a->blocksize - 1) / a->blocksize;
-  const long long ipb = ((a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1 + FILT_GROUP - 1) / FILT_GROUP;
+  const long long ipb = (a->blocksize / a->typesize + FILT_TILE - 1) / FILT_TILE + 1;
   long long ctas = (nblocks * ipb + FILT_WARPS - 1) / FILT_WARPS;
   if (ctas > 7) ctas = 7;          /* small odd grid: exercises the grid-stride loop */
   if (ctas < 1) ctas = 1;
   g_launches++;
   FilterArgs args = *a;
   simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(FILT_WARPS * 32), bit ? FILT_WARPS * 16 * FILT_TILE : 0,
-               [&] { filter_kernel(args); });
+               [&] { if (args.typesize == 4) filter_kernel<4>(args); else filter_kernel<0>(args); });
   return 0;
 }
 

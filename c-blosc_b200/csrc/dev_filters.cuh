@@ -90,30 +90,43 @@ DEV void planes_to_store4(u8* __restrict__ p, const u32 (&pl)[TS]) {
   }
 }
 
-/* ---- fast tile paths: a full tile of FILT_TILE elements starting at element e0 ---- */
+/* ---- fast tile paths: a full tile of FILT_TILE elements starting at element e0 ----
+ * All the loads of a batch of iterations are issued before the first transpose / store, so that a lane has
+ * 64-128 bytes in flight whatever the typesize (the copy is latency-bound otherwise: 8 bytes per lane and
+ * iteration at typesize 2). */
 template <int TS>
 DEV void tile_shuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e0) {
   const int lane = lane_id();
-#pragma unroll 4
-  for (int q = 0; q < FILT_TILE / 128; q++) {
-    const int e = e0 + q * 128 + 4 * lane;
-    u32 pl[TS];
-    load4_to_planes<TS>(s + (long long)e * TS, pl);
+  constexpr int B = TS <= 4 ? 8 : (TS == 8 ? 4 : 2);          /* iterations per batch */
+#pragma unroll 1
+  for (int q0 = 0; q0 < FILT_TILE / 128; q0 += B) {
+    u32 pl[B][TS];
 #pragma unroll
-    for (int j = 0; j < TS; j++) *(u32*)(d + (long long)j * N + e) = pl[j];
+    for (int q = 0; q < B; q++) load4_to_planes<TS>(s + (long long)(e0 + (q0 + q) * 128 + 4 * lane) * TS, pl[q]);
+#pragma unroll
+    for (int q = 0; q < B; q++) {
+      const int e = e0 + (q0 + q) * 128 + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < TS; j++) *(u32*)(d + (long long)j * N + e) = pl[q][j];
+    }
   }
 }
 
 template <int TS>
 DEV void tile_unshuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e0) {
   const int lane = lane_id();
-#pragma unroll 4
-  for (int q = 0; q < FILT_TILE / 128; q++) {
-    const int e = e0 + q * 128 + 4 * lane;
-    u32 pl[TS];
+  constexpr int B = TS <= 4 ? 8 : 2;
+#pragma unroll 1
+  for (int q0 = 0; q0 < FILT_TILE / 128; q0 += B) {
+    u32 pl[B][TS];
 #pragma unroll
-    for (int j = 0; j < TS; j++) pl[j] = *(const u32*)(s + (long long)j * N + e);
-    planes_to_store4<TS>(d + (long long)e * TS, pl);
+    for (int q = 0; q < B; q++) {
+      const int e = e0 + (q0 + q) * 128 + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < TS; j++) pl[q][j] = *(const u32*)(s + (long long)j * N + e);
+    }
+#pragma unroll
+    for (int q = 0; q < B; q++) planes_to_store4<TS>(d + (long long)(e0 + (q0 + q) * 128 + 4 * lane) * TS, pl[q]);
   }
 }
 
@@ -122,6 +135,7 @@ template <int TS>
 DEV void tile_bitshuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e0, u8* sm) {
   const int lane = lane_id();
   const int rowlen = N >> 3;
+#pragma unroll 4
   for (int q = 0; q < FILT_TILE / 128; q++) {
     const int el = q * 128 + 4 * lane;
     u32 pl[TS];
@@ -154,6 +168,7 @@ template <int TS>
 DEV void tile_bitunshuffle(const u8* __restrict__ s, u8* __restrict__ d, int N, int e0, u8* sm) {
   const int lane = lane_id();
   const int rowlen = N >> 3;
+#pragma unroll 2
   for (int j = 0; j < TS; j++) {
     const u8* row = s + (long long)(8 * j) * rowlen + (e0 >> 3) + 4 * lane;
     u32 lo0 = *(const u32*)(row);

@@ -98,6 +98,25 @@ def test_small_and_ragged_sizes(pkg, orc, cuda, n):
             assert dn == n and (out[:n] == src).all()
 
 
+def test_baseline_cfg1_memcpyed_1mib(pkg, orc, cuda):
+    """BASELINE.json configs[0]: 1 MiB, typesize 4, shuffle, clevel 0 -> a MEMCPYED chunk of nbytes+16 with blocksize 8192 and
+    no filter applied (blosc.c:825-830), identical to the oracle's, from host and from device pointers."""
+    torch = cuda
+    n = 1 << 20
+    src = gen("rand", n, seed=11)
+    want_n, want = compress(orc, "orc_compress_ctx", 0, 1, 4, src, n + 16, "blosclz")
+    got_n, got = _gpu_compress(pkg, 0, 1, 4, src, n + 16, "blosclz")
+    assert got_n == want_n == n + 16 and (got[:got_n] == want[:want_n]).all()
+    assert got[2] & 0x2 and int.from_bytes(bytes(got[8:12]), "little") == 8192 and (got[16:16 + n] == src).all()
+    d_src = torch.from_numpy(src).cuda()
+    d_chunk = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+    assert pkg.compress_ctx(0, 1, 4, n, d_src, d_chunk, n + 16, "lz4") == n + 16
+    d_out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert pkg.decompress_ctx(d_chunk, d_out, n) == n and torch.equal(d_out, d_src)
+    dn, out = _gpu_decompress(pkg, got, n)
+    assert dn == n and (out[:n] == src).all()
+
+
 def test_maxout_semantics(pkg, cuda):
     """tests/test_maxout.c:26-143."""
     n = 1000 * 1000

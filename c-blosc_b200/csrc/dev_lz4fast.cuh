@@ -38,9 +38,6 @@
 #endif
 #define FAST_LAZY 0                  /* matches shorter than this are checked against the next position's match */
 #define FAST_NICE 4096                  /* a match this long is taken without walking the chain */
-#ifndef HMASK
-#define HMASK 0xffffu
-#endif
 #define FAST_MFLIMIT 12               /* lz4.c:239-243: the last match starts >= 12 bytes before the end ... */
 #define FAST_LASTLITERALS 5           /* ... and the last 5 bytes are literals */
 
@@ -84,13 +81,14 @@ DEV u32 fast_ld8(const FastView& v, int p) {
   return (fast_word(v, q >> 2) >> ((u32)(q & 3) * 8u)) & 0xffu;
 }
 
-DEV u32 fast_hash(u32 word, u32 b4) { return ((word * 2654435761u) ^ (b4 * 2246822519u)) >> (32 - FAST_HLOG); }
+/* hash of the 6 bytes word | b45 << 32 (b45 = the two bytes that follow the word) */
+DEV u32 fast_hash(u32 word, u32 b45) { return ((word * 2654435761u) ^ (b45 * 2246822519u)) >> (32 - FAST_HLOG); }
 
 /* ---- index: prev[p] for every position of one stream, by one warp ----
  * Every step takes FAST_BATCH = 128 positions (4 consecutive ones per lane): hash, look the table up (state as of
  * the end of the previous step), then enter the 128 positions (atomicMax: the highest position wins, whatever the
  * order of the lanes).  A lane loads ONE aligned word per step -- its neighbours' words arrive by shuffle -- and the
- * word of the next step is requested before this step's table work, so the only latency on the step-to-step
+ * words of the next two steps are requested before this step's table work, so the only latency on the step-to-step
  * chain is the shared-memory round trip.  Table entries are positions; "empty" is a position so far back that
  * the distance test rejects it. */
 #define FAST_EMPTY (-(1 << 20))
@@ -102,7 +100,7 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
   const FastView v = fast_view(s, n);
   const bool vec = (((uintptr_t)prev) & 7u) == 0;
   const u32 sh = (u32)v.sal * 8u;
-  /* lane's word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane.  The step uses its own words and two words
+  /* lane's word of a step: (base + 4 lane + sal) >> 2 = base/4 + lane.  The step uses its own words and three words
    * of the next step: both were requested at least a step ago, and one lane pulls the line of eight steps ahead
    * into L1, so that no step waits for DRAM. */
   u32 cur = fast_word(v, lane), nxt = fast_word(v, (FAST_BATCH >> 2) + lane);
@@ -114,21 +112,18 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
 #ifndef SIMT_EMU
     if (lane == 0 && base + 10 * FAST_BATCH < n) asm volatile("prefetch.global.L1 [%0];" :: "l"(s + base + 8 * FAST_BATCH));
 #endif
-    /* the two words behind the lane's own: the next lanes' words, or the first words of the next step */
-    const u32 d1 = __shfl_down_sync(FULLMASK, w0, 1), d2 = __shfl_down_sync(FULLMASK, w0, 2);
-    const u32 e0 = __shfl_sync(FULLMASK, cur, 0), e1 = __shfl_sync(FULLMASK, cur, 1);
-    const u32 w1 = lane < 31 ? d1 : e0, w2 = lane < 30 ? d2 : (lane == 30 ? e0 : e1);
-    /* bytes p0 .. p0+7 */
-    const u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh);
-    const u32 w3d = __shfl_down_sync(FULLMASK, w0, 3); const u32 w3e = __shfl_sync(FULLMASK, cur, (lane + 3) & 31); const u32 w2x = __funnelshift_r(w2, lane < 29 ? w3d : w3e, sh);
+    /* the three words behind the lane's own: the next lanes' words, or the first words of the next step */
+    const u32 d1 = __shfl_down_sync(FULLMASK, w0, 1), d2 = __shfl_down_sync(FULLMASK, w0, 2), d3 = __shfl_down_sync(FULLMASK, w0, 3);
+    const u32 e1 = __shfl_sync(FULLMASK, cur, (lane + 1) & 31), e2 = __shfl_sync(FULLMASK, cur, (lane + 2) & 31),
+              e3 = __shfl_sync(FULLMASK, cur, (lane + 3) & 31);
+    const u32 w1 = lane < 31 ? d1 : e1, w2 = lane < 30 ? d2 : e2, w3 = lane < 29 ? d3 : e3;
+    /* bytes p0 .. p0+11 */
+    const u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
     u32 h[4];
     int c[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const u32 word = __funnelshift_r(v0, v1, 8u * j);
-      h[j] = fast_hash(word, HMASK & (j == 0 ? v1 : __funnelshift_r(v1, w2x, 8u * j)));
-    }
-    const bool full = base + FAST_BATCH + 8 <= n;  /* every position of the step has its 8 bytes inside the stream */
+    for (int j = 0; j < 4; j++)
+      h[j] = fast_hash(__funnelshift_r(v0, v1, 8u * j), __funnelshift_r(v1, v2, 8u * j) & 0xffffu);
     if (base == 0) {
       /* the first batch has nothing in front of it: resolve it position by position, so that a run or a
        * short period at the very start of a stream is found from its second occurrence on */
@@ -142,21 +137,29 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
         }
         __syncwarp();
       }
-    } else {
+    } else if (base + FAST_BATCH + 8 <= n) {        /* every position of the step has its 8 bytes inside the stream */
 #pragma unroll
-      for (int j = 0; j < 4; j++) c[j] = (full || p0 + j + 8 <= n) ? tab[h[j]] : FAST_EMPTY;
+      for (int j = 0; j < 4; j++) c[j] = tab[h[j]];
       __syncwarp();
       /* a run (every position of the step hashes alike -- the zero planes of shuffled data) would make the
        * 128 atomics collide on one word: the last position enters it alone */
       const u32 hl = __shfl_sync(FULLMASK, h[3], 0);
       const bool same = h[0] == h[1] && h[1] == h[2] && h[2] == h[3] && h[3] == hl;
-      if (full && __all_sync(FULLMASK, same)) {
+      if (__all_sync(FULLMASK, same)) {
         if (lane == 31) tab[h[3]] = p0 + 3;
       } else {
 #pragma unroll
         for (int j = 0; j < 4; j++)
-          if ((full || p0 + j + 8 <= n) && (j == 3 || h[j] != h[j + 1])) atomicMax(&tab[h[j]], p0 + j);
+          if (j == 3 || h[j] != h[j + 1]) atomicMax(&tab[h[j]], p0 + j);
       }
+      __syncwarp();
+    } else {                                          /* the last step(s) of the stream */
+#pragma unroll
+      for (int j = 0; j < 4; j++) c[j] = p0 + j + 8 <= n ? tab[h[j]] : FAST_EMPTY;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (p0 + j + 8 <= n) atomicMax(&tab[h[j]], p0 + j);
       __syncwarp();
     }
     u32 d[4];

@@ -36,6 +36,9 @@
 #ifndef FAST_SMALL
 #define FAST_SMALL 4
 #endif
+#ifndef FAST_BUDGET
+#define FAST_BUDGET 12
+#endif
 #define FAST_LAZY 0                  /* matches shorter than this are checked against the next position's match */
 #define FAST_NICE 4096                  /* a match this long is taken without walking the chain */
 #define FAST_MFLIMIT 12               /* lz4.c:239-243: the last match starts >= 12 bytes before the end ... */
@@ -276,6 +279,7 @@ DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__
   int ip = a, anchor = a, op = 0, l1 = 0, miss = 0;
   int lt = 0, lm = 0, lo = 0;                    /* last sequence: token position in the slot, match length, offset */
   int step = 1, snb = accel << 6;                /* LZ4's skip schedule (lz4.c:1043-1053) */
+  int nsearch = 0;
   bool first = true;
   /* `rep`: an offset worth trying before the chain.  Inside a segment it is the offset of the last match (periodic
    * data: the match that a glitch ended resumes right behind it).  At the start of a segment it is whichever chain
@@ -301,6 +305,9 @@ DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__
   }
   while (ip <= mfl) {
     int de = depth >> ((miss >> 3) < 5 ? (miss >> 3) : 5);   /* a run of misses (incompressible data) shortens the chain walk */
+    if (nsearch >= FAST_BUDGET) de >>= 1;                     /* the slowest segment of a window sets its time: a segment that needs many searches walks shorter chains */
+    if (nsearch >= 2 * FAST_BUDGET) de >>= 1;
+    nsearch++;
     if (de < 2) de = 2;
     int boff = 0;
     int best = lz4f_search(v, prev, ip, mlim, rep, ip == a ? pre : 0, de, &boff);

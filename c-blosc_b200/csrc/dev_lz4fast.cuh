@@ -124,6 +124,20 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
     const u32 v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
     u32 h[4];
     int c[4];
+    /* a step inside a run of one byte value (the zero planes of shuffled data are nothing else): every position has
+     * the same hash, one lookup and one table store serve the whole step */
+    const u32 b0 = __shfl_sync(FULLMASK, v0, 0);
+    const bool runstep = base != 0 && base + FAST_BATCH + 8 <= n &&
+                         __all_sync(FULLMASK, v0 == b0 && v1 == b0 && v2 == b0 && b0 == __funnelshift_r(b0, b0, 8));
+    if (runstep) {
+      const u32 hr = fast_hash(b0, b0 & 0xffffu);
+      const int cr = tab[hr];
+      __syncwarp();
+      if (lane == 31) tab[hr] = p0 + 3;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; j++) c[j] = cr;
+    } else {
 #pragma unroll
     for (int j = 0; j < 4; j++)
       h[j] = fast_hash(__funnelshift_r(v0, v1, 8u * j), __funnelshift_r(v1, v2, 8u * j) & 0xffffu);
@@ -164,6 +178,7 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
       for (int j = 0; j < 4; j++)
         if (p0 + j + 8 <= n) atomicMax(&tab[h[j]], p0 + j);
       __syncwarp();
+    }
     }
     u32 d[4];
 #pragma unroll

@@ -722,7 +722,8 @@ static long long g_dbg_lz4d_batch_seqs = 0, g_dbg_lz4d_fast_seqs = 0, g_dbg_lz4d
 #define LZ4D_RING 16384                      /* bytes of recent output mirrored in shared memory, per warp */
 #define LZ4D_RMASK (LZ4D_RING - 1)
 #define LZ4D_BATCH_OUT 320                   /* a batch writes < 320 bytes (11 sequences x <= 27) */
-#define LZ4D_DENSE_OUT 1664                  /* a dense step writes <= 28 x 18 + 4 x 273 bytes */
+#define LZ4D_DENSE_LONG 8                    /* long matches (one extra length byte) a dense step takes inline */
+#define LZ4D_DENSE_OUT 2624                  /* a dense step writes <= 24 x 18 + 8 x 273 bytes */
 #define LZ4D_DENSE_MIN 4                     /* fewer chained 3-byte sequences than this: the 11-wide batch path is as good */
 #define LZ4D_SCRATCH 256                     /* per-warp shared scratch after the ring: sequence table + start-bit words */
 #define LZ4D_SMEM (LZ4D_RING + LZ4D_SCRATCH)
@@ -758,8 +759,8 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
      * output byte are independent, and every lane copies its own match. */
     if (dense_skip > 0) dense_skip--;
     else if (ip + 112 <= iend && op + LZ4D_DENSE_OUT <= oend - LZ4_MFLIMIT) {
-      u32 b0, b1;
-      ldp_win8(ib, ip + 3 * lane, b0, b1);                    /* bytes ip+3l .. ip+3l+7 (touches < ip+105) */
+      u32 b0, b1, b2;
+      ldp_win12(ib, ip + 3 * lane, b0, b1, b2);               /* bytes ip+3l .. ip+3l+11 (touches < ip+109) */
       lz4d_prefetch(in, ip + 256 + 128 * lane, lane < 2 ? iend : 0);
       /* Segments: lanes [c, e) see 3-byte sequences at byte shift s; the sequence that ends a
        * segment is very often a longer literal-free match with one extra length byte (token 0x0F,
@@ -773,13 +774,13 @@ DEV int lz4_decode_warp(const u8* __restrict__ in, const int csize, u8* out, con
         const int e = stop ? __ffs((int)stop) - 1 : 32;
         if (lane >= c && lane < e) { kind = 1; ml = (int)(tok & 15u) + 4; off = (int)((w >> 8) & 0xffffu); }
         c = e;
-        if (e >= 32 || sft == 4) break;
+        if (e >= 32 || sft == LZ4D_DENSE_LONG) break;
         const u32 tw = __shfl_sync(FULLMASK, w, e);
         if ((tw & 0xffu) != 0x0fu || (tw >> 24) == 255u) break;
         if (lane == e) { kind = 2; ml = 19 + (int)(tw >> 24); off = (int)((tw >> 8) & 0xffffu); }
         c = e + 1; sft++;
         if (c >= 32) break;
-        w = __funnelshift_r(b0, b1, 8u * (u32)sft);
+        w = sft < 4 ? __funnelshift_r(b0, b1, 8u * (u32)sft) : (sft == 4 ? b1 : (sft < 8 ? __funnelshift_r(b1, b2, 8u * (u32)(sft - 4)) : b2));
       }
       int cnt = c;                                             /* lanes [0, cnt) hold one sequence each */
       int incl = ml;

@@ -98,6 +98,8 @@ typedef struct FastArgs {
   int win_bytes;                   /* bytes per parse window (one CTA, one thread per segment): multiple of 32 segments */
   int groups_full, groups_left;    /* windows per full stream / of the leftover stream */
   int depth, accel;
+  int hash_mask;                   /* 0xffff: chains over 6-byte hashes (lz4); 0: over 4-byte hashes (lz4hc) */
+  int lazy;                        /* matches shorter than this are weighed against the next position's match (lz4hc) */
   int* queue;
   unsigned queue_base;
   unsigned* queue_base_host;

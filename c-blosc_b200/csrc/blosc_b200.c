@@ -285,17 +285,18 @@ int blosc_compcode_to_compname(int compcode, const char** compname) {    /* blos
                                  BLOSC_SNAPPY_COMPNAME, BLOSC_ZLIB_COMPNAME, BLOSC_ZSTD_COMPNAME};
   *compname = (compcode >= 0 && compcode < 6) ? names[compcode] : NULL;
   /* codecs this build can ENCODE; like a reference built without the others */
-  if (compcode == BLOSC_BLOSCLZ || compcode == BLOSC_LZ4) return compcode;
+  if (compcode == BLOSC_BLOSCLZ || compcode == BLOSC_LZ4 || compcode == BLOSC_LZ4HC) return compcode;
   return -1;
 }
 
 int blosc_compname_to_compcode(const char* compname) {                    /* blosc.c:377-409 */
   if (strcmp(compname, BLOSC_BLOSCLZ_COMPNAME) == 0) return BLOSC_BLOSCLZ;
   if (strcmp(compname, BLOSC_LZ4_COMPNAME) == 0) return BLOSC_LZ4;
+  if (strcmp(compname, BLOSC_LZ4HC_COMPNAME) == 0) return BLOSC_LZ4HC;
   return -1;
 }
 
-const char* blosc_list_compressors(void) { return BLOSC_BLOSCLZ_COMPNAME "," BLOSC_LZ4_COMPNAME; }   /* blosc.c:2033-2056 */
+const char* blosc_list_compressors(void) { return BLOSC_BLOSCLZ_COMPNAME "," BLOSC_LZ4_COMPNAME "," BLOSC_LZ4HC_COMPNAME; }   /* blosc.c:2033-2056 */
 const char* blosc_get_version_string(void) { return BLOSC_VERSION_STRING; }
 
 int blosc_get_complib_info(const char* compname, char** complib, char** version) {   /* blosc.c:2063-2124 */
@@ -573,6 +574,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
   /* write_compression_header, blosc.c:1148-1247 */
   if (compcode == BLOSC_BLOSCLZ) compformat = BLOSC_BLOSCLZ_FORMAT;
   else if (compcode == BLOSC_LZ4) compformat = BLOSC_LZ4_FORMAT;
+  else if (compcode == BLOSC_LZ4HC) compformat = BLOSC_LZ4HC_FORMAT;     /* blosc.c:1170-1172: the LZ4 format */
   else {
     fprintf(stderr, "Blosc has not been compiled with '%s' ", compressor ? compressor : "(null)");
     fprintf(stderr, "compression support.  Please use one having it.");
@@ -633,7 +635,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
     if (buf_ensure(&w->needs, (size_t)ea.map.nstreams * 4 + 64)) break;
     if (buf_ensure(&w->bstarts, (size_t)nblocks * 4 + 64)) break;
     ea.in = d_codec_in; ea.slots = (uint8_t*)w->slots.p; ea.csizes = (int*)w->csizes.p; ea.needs = (int*)w->needs.p;
-    ea.codec = compcode == BLOSC_LZ4 ? B2_CODEC_LZ4 : B2_CODEC_BLOSCLZ;
+    ea.codec = (compcode == BLOSC_LZ4 || compcode == BLOSC_LZ4HC) ? B2_CODEC_LZ4 : B2_CODEC_BLOSCLZ;
     ea.clevel = clevel; ea.accel = 10 - clevel;                          /* blosc.c:577-587 */
     ea.split_flag = !dont_split;
     ea.many = (pl && pl->many) || ws_busy(w->dev) > 1;      /* a frame, or other _ctx calls running on this device */
@@ -655,7 +657,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
     ea.scan = sa;
     launched = 1;
     memset(&ca, 0, sizeof ca);
-    if (ea.codec == B2_CODEC_LZ4 && lz4_fast_wanted()) {
+    if (ea.codec == B2_CODEC_LZ4 && (compcode == BLOSC_LZ4HC || lz4_fast_wanted())) {
       FastArgs fx;
       const int neblock = bs / nsplits;
       memset(&fx, 0, sizeof fx);
@@ -670,6 +672,15 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
         fx.groups_full = (neblock + win - 1) / win; fx.groups_left = (leftover + win - 1) / win;
       }
       fx.depth = 3 * clevel + 1; fx.accel = ea.accel;
+      /* "lz4hc" (blosc.c:422-433 hands clevel to LZ4_compress_HC): the same hash-chain parser, with LZ4HC's search
+       * effort -- 2^(level-1) candidates, capped -- and no skipping over literals */
+      fx.hash_mask = 0xffff; fx.lazy = 0;
+      if (compcode == BLOSC_LZ4HC) {
+        fx.depth = clevel <= 2 ? 4 : (clevel >= 8 ? 128 : (1 << (clevel - 1))); fx.accel = 1;
+        fx.hash_mask = 0xffff; fx.lazy = 64;
+        { const char* e = getenv("BLOSC_B200_HC_HASHMASK"); if (e) fx.hash_mask = (int)strtol(e, NULL, 0); }
+        { const char* e = getenv("BLOSC_B200_HC_LAZY"); if (e) fx.lazy = atoi(e); }
+      }
       { const char* e = getenv("BLOSC_B200_FAST_DEPTH"); if (e && atoi(e) > 0) fx.depth = atoi(e); }   /* experiments */
       if (buf_ensure(&w->prev, 2 * (size_t)nb + 64)) break;
       if (buf_ensure(&w->segs, ((size_t)nfull * nsplits * fx.segs_full + fx.segs_left + 8) * sizeof(FastSeg))) break;
@@ -1117,7 +1128,7 @@ long long blosc_b200_frame_compress(int clevel, int doshuffle, size_t typesize, 
   if (clevel < 0 || clevel > 9) return -10;                       /* same codes as the chunk API */
   if (doshuffle != 0 && doshuffle != 1 && doshuffle != 2) return -10;
   if (typesize == 0) return -10;
-  if (blosc_compname_to_compcode(compressor) != BLOSC_BLOSCLZ && blosc_compname_to_compcode(compressor) != BLOSC_LZ4) return -5;
+  if (blosc_compname_to_compcode(compressor) < 0) return -5;
   chunksize = frame_chunksize(chunksize, typesize);
   nchunks = (nbytes + chunksize - 1) / chunksize;
   if (nchunks > 0x7fffffff / 2) return -1;

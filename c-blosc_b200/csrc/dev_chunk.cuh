@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(INDEX_WARPS * 32) index_kernel(FastArgs a) {
     int block, len, split;
     long long off;
     stream_locate(a.map, idx, &block, &off, &len, &split);
-    lz4f_index_warp(a.in + off, len, a.prev + off, tab);
+    lz4f_index_warp(a.in + off, len, a.prev + off, tab, (u32)a.hash_mask);
     __syncwarp();
   }
 }
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 3) parse_kernel(Fa
     const int k = g * spw + tid;
     if (k < K && tid < spw) {
       const int sa = k * FAST_SEG, sb = sa + FAST_SEG < len ? sa + FAST_SEG : len;
-      lz4f_parse_lane(v, len, a.prev + off, sa, sb, a.slots + off + sa, &segs[k], a.depth, a.accel);
+      lz4f_parse_lane(v, len, a.prev + off, sa, sb, a.slots + off + sa, &segs[k], a.depth, a.accel, a.lazy);
     }
     __syncthreads();                               /* shared memory may be reused */
   }

@@ -39,7 +39,6 @@
 #ifndef FAST_BUDGET
 #define FAST_BUDGET 12
 #endif
-#define FAST_LAZY 0                  /* matches shorter than this are checked against the next position's match */
 #define FAST_NICE 4096                  /* a match this long is taken without walking the chain */
 #define FAST_MFLIMIT 12               /* lz4.c:239-243: the last match starts >= 12 bytes before the end ... */
 #define FAST_LASTLITERALS 5           /* ... and the last 5 bytes are literals */
@@ -84,7 +83,8 @@ DEV u32 fast_ld8(const FastView& v, int p) {
   return (fast_word(v, q >> 2) >> ((u32)(q & 3) * 8u)) & 0xffu;
 }
 
-/* hash of the 6 bytes word | b45 << 32 (b45 = the two bytes that follow the word) */
+/* hash of the 4..6 bytes word | b45 << 32 (b45 = the bytes that follow the word, masked: 0xffff = 6-byte hash, the LZ4 fast
+ * setting; 0 = 4-byte hash = LZ4's MINMATCH, the "lz4hc" setting) */
 DEV u32 fast_hash(u32 word, u32 b45) { return ((word * 2654435761u) ^ (b45 * 2246822519u)) >> (32 - FAST_HLOG); }
 
 /* ---- index: prev[p] for every position of one stream, by one warp ----
@@ -95,7 +95,7 @@ DEV u32 fast_hash(u32 word, u32 b45) { return ((word * 2654435761u) ^ (b45 * 224
  * chain is the shared-memory round trip.  Table entries are positions; "empty" is a position so far back that
  * the distance test rejects it. */
 #define FAST_EMPTY (-(1 << 20))
-DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict__ prev, u32* tabmem) {
+DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict__ prev, u32* tabmem, const u32 hmask) {
   int* tab = (int*)tabmem;
   const int lane = lane_id();
   for (int i = lane; i < (1 << FAST_HLOG); i += 32) tab[i] = FAST_EMPTY;
@@ -130,7 +130,7 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
     const bool runstep = base != 0 && base + FAST_BATCH + 8 <= n &&
                          __all_sync(FULLMASK, v0 == b0 && v1 == b0 && v2 == b0 && b0 == __funnelshift_r(b0, b0, 8));
     if (runstep) {
-      const u32 hr = fast_hash(b0, b0 & 0xffffu);
+      const u32 hr = fast_hash(b0, b0 & hmask);
       const int cr = tab[hr];
       __syncwarp();
       if (lane == 31) tab[hr] = p0 + 3;
@@ -140,7 +140,7 @@ DEV void lz4f_index_warp(const u8* __restrict__ s, const int n, u16* __restrict_
     } else {
 #pragma unroll
     for (int j = 0; j < 4; j++)
-      h[j] = fast_hash(__funnelshift_r(v0, v1, 8u * j), __funnelshift_r(v1, v2, 8u * j) & 0xffffu);
+      h[j] = fast_hash(__funnelshift_r(v0, v1, 8u * j), __funnelshift_r(v1, v2, 8u * j) & hmask);
     if (base == 0) {
       /* the first batch has nothing in front of it: resolve it position by position, so that a run or a
        * short period at the very start of a stream is found from its second occurrence on */
@@ -287,7 +287,7 @@ DEV int lz4f_search(const FastView& v, const u16* __restrict__ prev, const int i
  * be continued by the segments that follow (runs, periodic data), so its final length is only known to the
  * stream scan. */
 DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__ prev, const int a, const int b,
-                         u8* __restrict__ slot, FastSeg* rec, const int depth, const int accel) {
+                         u8* __restrict__ slot, FastSeg* rec, const int depth, const int accel, const int lazy) {
   int mfl = b - 4, mlim = b;                     /* last position a match may start at; first byte it may not cover */
   if (mfl > n - FAST_MFLIMIT) mfl = n - FAST_MFLIMIT;
   if (mlim > n - FAST_LASTLITERALS) mlim = n - FAST_LASTLITERALS;
@@ -326,7 +326,7 @@ DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__
     if (de < 2) de = 2;
     int boff = 0;
     int best = lz4f_search(v, prev, ip, mlim, rep, ip == a ? pre : 0, de, &boff);
-    if (best >= 4 && best < FAST_LAZY && ip + 1 <= mfl) {
+    if (best >= 4 && best < lazy && ip + 1 <= mfl) {
       /* lazy evaluation (as LZ4HC / zlib): a short match is given up for a literal when the next position
        * starts a longer one */
       int boff2 = 0;

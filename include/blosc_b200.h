@@ -12,10 +12,12 @@
  *     GPU-resident caller never leaves HBM;
  *   - `numinternalthreads` is validated like the reference but otherwise ignored: the
  *     CUDA grid is the thread pool (reference blosc.c:1706-1949);
- *   - compressors other than "blosclz" and "lz4" report -5 exactly like a reference built
- *     with -DDEACTIVATE_ZLIB/ZSTD/SNAPPY (blosc.c:573,1197-1208).  Decoding is wider: LZ4HC
- *     chunks decode (same block format) and so do zlib and zstd chunks (serial GPU decoders,
- *     one lane per stream); snappy chunks report -5;
+ *   - "blosclz" and "lz4" chunks are byte-identical to the reference's; "lz4hc" is accepted and
+ *     written in its (= LZ4's, blosc.h:96) format by a hash-chain parser run with LZ4HC's search
+ *     effort -- every reference build decodes the chunks, the header is the reference's, the
+ *     bytes are not LZ4_compress_HC's; other compressors report -5 exactly like a reference built
+ *     with -DDEACTIVATE_ZLIB/ZSTD/SNAPPY (blosc.c:573,1197-1208).  Decoding is wider: zlib and
+ *     zstd chunks decode too (serial GPU decoders, one lane per stream); snappy chunks report -5;
  *   - there is no CPU codec: without a CUDA device every compress/decompress call
  *     prints a message on stderr and returns -1.
  */

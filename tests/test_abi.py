@@ -66,7 +66,8 @@ def test_host_only_entry_points(pkg):
     lib.blosc_cbuffer_complib.restype = C.c_char_p
     assert lib.blosc_cbuffer_complib(chunk.ctypes.data_as(C.c_void_p)) == b"LZ4"
     lib.blosc_list_compressors.restype = C.c_char_p
-    assert lib.blosc_list_compressors() == b"blosclz,lz4"
+    assert lib.blosc_list_compressors() == b"blosclz,lz4,lz4hc"
+    assert lib.blosc_compname_to_compcode(b"lz4hc") == 2
 
 
 def test_product_does_not_touch_the_oracle():

@@ -87,6 +87,37 @@ def test_emu_fast_is_opt_in(emu, orc):
     assert g == w and (got[:g] == want[:w]).all()
 
 
+def _check_lz4hc(lib, ref, src, ts, shuf, clevel, gpu=None):
+    n = len(src)
+    want_n, want = compress(ref, "blosc_compress_ctx", clevel, shuf, ts, src, n + 16, "lz4hc")
+    if gpu is None:
+        r, chunk = compress(lib, "blosc_compress_ctx", clevel, shuf, ts, src, n + 16, "lz4hc")
+    else:
+        r, chunk = gpu
+    assert r > 0 and (chunk[r:] == 0xAA).all()
+    dn, out = decompress(ref, "blosc_decompress_ctx", chunk, n)
+    assert dn == n and (out[:n] == src).all()
+    memcpyed = lambda c: bool(c[2] & 0x2)
+    if not memcpyed(chunk) and not memcpyed(want):
+        # same header as the reference's lz4hc chunk: format version, LZ4 format id + flags, typesize, nbytes, blocksize
+        assert bytes(chunk[:12]) == bytes(want[:12]), (bytes(chunk[:12]).hex(), bytes(want[:12]).hex())
+    return r, want_n
+
+
+def test_emu_lz4hc_chunks(emu, ref):
+    """blosc_compress_ctx(..., "lz4hc", ...) (blosc.c:422-433).  The chunks are LZ4-format
+    (LZ4HC and LZ4 share it, blosc.h:96) from the hash-chain parser run with LZ4HC's search effort; the reference decodes
+    them, the header is the reference's, and the size stays within 1.6x of LZ4_compress_HC's on compressible data."""
+    os.environ.pop("BLOSC_B200_PARSE", None)
+    for kind in ("bench", "f32", "i32", "lowent", "zeros", "mixed", "rand", "text"):
+        for n in (1 << 20, 300001, 5000):
+            src = gen(kind, n)
+            for ts, shuf, clevel in ((4, 1, 5), (8, 1, 9), (1, 0, 1), (2, 2, 3)):
+                got, want = _check_lz4hc(emu, ref, src, ts, shuf, clevel)
+                if kind in ("bench", "i32", "lowent", "zeros", "mixed") and n >= 300001 and want < n // 2:
+                    assert got <= 1.6 * want, (kind, n, ts, shuf, clevel, got, want)
+
+
 # ---------------------------------------------------------------- GPU
 def _gpu_compress(pkg, clevel, shuf, ts, src, destsize, comp, bs=0):
     dest = np.full(destsize + 64, 0xAA, np.uint8)
@@ -111,6 +142,27 @@ def test_gpu_fast_chunks_decode_with_the_oracle(pkg, orc, cuda, fast_env, kind):
             _check(chunk, r, n, src, decoders)
             out = np.zeros(n + 64, np.uint8)
             assert pkg.decompress_ctx(chunk, out, n) == n and (out[:n] == src).all()
+
+
+@pytest.mark.gpu
+def test_gpu_lz4hc_chunks(pkg, emu, cuda):
+    ref_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libblosc_ref.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref did not travel")
+    import ctypes as C
+    ref = C.CDLL(ref_path)
+    ref.blosc_compress_ctx.restype = C.c_int; ref.blosc_decompress_ctx.restype = C.c_int
+    os.environ.pop("BLOSC_B200_PARSE", None)
+    for kind in ("bench", "f32", "zeros", "mixed", "rand"):
+        for n in (4 << 20, 300001):
+            src = gen(kind, n)
+            for ts, shuf, clevel in ((4, 1, 5), (8, 1, 9), (2, 2, 3)):
+                g = _gpu_compress(pkg, clevel, shuf, ts, src, n + 16, "lz4hc")
+                _check_lz4hc(None, ref, src, ts, shuf, clevel, gpu=g)
+                w, want = compress(emu, "blosc_compress_ctx", clevel, shuf, ts, src, n + 16, "lz4hc")
+                assert g[0] == w and (g[1][:w] == want[:w]).all()          # deterministic: GPU == emulator
+                out = np.zeros(n + 64, np.uint8)
+                assert pkg.decompress_ctx(g[1], out, n) == n and (out[:n] == src).all()
 
 
 @pytest.mark.gpu

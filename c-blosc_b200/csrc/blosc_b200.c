@@ -668,6 +668,8 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
         const int longest = neblock > leftover ? neblock : leftover;
         int win = (longest + 32 * B2_FAST_SEG - 1) / (32 * B2_FAST_SEG) * (32 * B2_FAST_SEG);
         if (win > B2_FAST_WIN_MAX) win = B2_FAST_WIN_MAX;
+        { const char* e = getenv("BLOSC_B200_FAST_WIN"); const int v = e ? atoi(e) : 0;      /* experiments: smaller windows */
+          if (v >= 32 * B2_FAST_SEG && v < win) win = v / (32 * B2_FAST_SEG) * (32 * B2_FAST_SEG); }
         fx.win_bytes = win;
         fx.groups_full = (neblock + win - 1) / win; fx.groups_left = (leftover + win - 1) / win;
       }

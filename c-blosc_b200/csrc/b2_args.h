@@ -68,7 +68,9 @@ typedef struct EncodeArgs {
 } EncodeArgs;
 
 /* ---- segment-parallel LZ4 parse (dev_lz4fast.cuh) ---- */
+#ifndef B2_FAST_SEG
 #define B2_FAST_SEG 256     /* bytes per segment (dev_lz4fast.cuh FAST_SEG) */
+#endif
 #define B2_FAST_WIN_MAX (64 * 1024)   /* bytes of a stream that one parse CTA keeps in shared memory */
 typedef struct FastSeg {   /* one record per segment of FAST_SEG bytes */
   uint16_t nbytes;         /* bytes in the segment's slot (0: no match, the segment is all literals) */
@@ -95,7 +97,8 @@ typedef struct FastArgs {
   int* csizes;
   int* needs;
   int segs_full, segs_left;        /* segments per full stream / of the leftover stream */
-  int win_bytes;                   /* bytes per parse window (one CTA, one thread per segment): multiple of 32 segments */
+  int win_bytes;                   /* bytes per parse window (one CTA): multiple of 32 segments */
+  int threads;                     /* threads of a parse CTA (<= segments per window; they draw segments from a counter) */
   int groups_full, groups_left;    /* windows per full stream / of the leftover stream */
   int depth, accel;
   int hash_mask;                   /* 0xffff: chains over 6-byte hashes (lz4); 0: over 4-byte hashes (lz4hc) */

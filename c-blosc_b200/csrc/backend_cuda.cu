@@ -242,7 +242,7 @@ extern "C" int b2_launch_fast(const FastArgs* a, b2_stream_t s) {
   }
   {
     const long long njobs = (long long)a->map.nfull * a->map.nsplits * a->groups_full + a->groups_left;
-    const int threads = a->win_bytes / B2_FAST_SEG;
+    const int threads = a->threads;
     const size_t smem = (size_t)a->win_bytes + 64;
     int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));
     if (per_sm * threads > 2048) per_sm = 2048 / threads;

@@ -668,9 +668,8 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
         const int longest = neblock > leftover ? neblock : leftover;
         int win = (longest + 32 * B2_FAST_SEG - 1) / (32 * B2_FAST_SEG) * (32 * B2_FAST_SEG);
         if (win > B2_FAST_WIN_MAX) win = B2_FAST_WIN_MAX;
-        { const char* e = getenv("BLOSC_B200_FAST_WIN"); const int v = e ? atoi(e) : 0;      /* experiments: smaller windows */
-          if (v >= 32 * B2_FAST_SEG && v < win) win = v / (32 * B2_FAST_SEG) * (32 * B2_FAST_SEG); }
         fx.win_bytes = win;
+        fx.threads = win / B2_FAST_SEG;
         fx.groups_full = (neblock + win - 1) / win; fx.groups_left = (leftover + win - 1) / win;
       }
       fx.depth = 3 * clevel + 1; fx.accel = ea.accel;
@@ -680,10 +679,7 @@ static int compress_impl(int clevel, int doshuffle, size_t typesize, size_t nbyt
       if (compcode == BLOSC_LZ4HC) {
         fx.depth = clevel <= 2 ? 4 : (clevel >= 8 ? 128 : (1 << (clevel - 1))); fx.accel = 1;
         fx.hash_mask = 0xffff; fx.lazy = 64;
-        { const char* e = getenv("BLOSC_B200_HC_HASHMASK"); if (e) fx.hash_mask = (int)strtol(e, NULL, 0); }
-        { const char* e = getenv("BLOSC_B200_HC_LAZY"); if (e) fx.lazy = atoi(e); }
       }
-      { const char* e = getenv("BLOSC_B200_FAST_DEPTH"); if (e && atoi(e) > 0) fx.depth = atoi(e); }   /* experiments */
       if (buf_ensure(&w->prev, 2 * (size_t)nb + 64)) break;
       if (buf_ensure(&w->segs, ((size_t)nfull * nsplits * fx.segs_full + fx.segs_left + 8) * sizeof(FastSeg))) break;
       if (buf_ensure_zeroed(w, &w->seg_done, (size_t)ea.map.nstreams * 4 + 64)) break;

@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 3) parse_kernel(Fa
   const int tid = (int)threadIdx.x, lane = lane_id();
   const int nfs = a.map.nfull * a.map.nsplits;
   const int njobs = nfs * a.groups_full + a.groups_left;
-  const int spw = a.win_bytes / FAST_SEG;         /* segments per window = threads per CTA */
+  const int spw = a.win_bytes / FAST_SEG;         /* segments per window (the CTA has a.threads <= spw threads) */
   for (;;) {
-    if (tid == 0) sjob[0] = (int)((unsigned)atomicAdd(a.queue, 1) - a.queue_base);
+    if (tid == 0) { sjob[0] = (int)((unsigned)atomicAdd(a.queue, 1) - a.queue_base); sjob[1] = 0; }
     __syncthreads();
     const int job = sjob[0];
     if (job >= njobs) break;
@@ -295,8 +295,12 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 3) parse_kernel(Fa
     __syncthreads();
     v.sm = sdata; v.sm_lo = i_lo; v.sm_hi = i_hi;
     v.lo_pos = wa; v.bias = v.sal - 4 * i_lo;      /* position p is byte p + sal - 4 i_lo of the staged words */
-    const int k = g * spw + tid;
-    if (k < K && tid < spw) {
+    /* the threads draw the window's segments from a counter: a thread whose segment was cheap takes another one
+     * instead of waiting at the barrier for the slowest (the CTA may have fewer threads than the window has segments) */
+    for (;;) {
+      const int t = atomicAdd(&sjob[1], 1);
+      const int k = g * spw + t;
+      if (t >= spw || k >= K) break;
       const int sa = k * FAST_SEG, sb = sa + FAST_SEG < len ? sa + FAST_SEG : len;
       lz4f_parse_lane(v, len, a.prev + off, sa, sb, a.slots + off + sa, &segs[k], a.depth, a.accel, a.lazy);
     }

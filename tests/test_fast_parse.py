@@ -189,3 +189,31 @@ def test_gpu_fast_full_size_ratio_and_round_trip(pkg, cuda, fast_env):
         d_out.zero_()
         assert pkg.decompress_ctx(d_chunk, d_out, n) == n
         assert torch.equal(d_out, d_src)
+
+
+def test_emu_frames_with_fast_parse_and_lz4hc(emu, ref, fast_env):
+    """frames (several chunks in flight, each with its own chain index and segment records) written with the fast parse
+    and with "lz4hc": every chunk of the frame decodes with the unmodified reference, the frame round-trips"""
+    import ctypes as C
+    sz, ci, ll = C.c_size_t, C.c_int, C.c_longlong
+    emu.blosc_b200_frame_bound.restype = sz; emu.blosc_b200_frame_bound.argtypes = [sz, sz, sz]
+    emu.blosc_b200_frame_compress.restype = ll
+    emu.blosc_b200_frame_compress.argtypes = [ci, ci, sz, sz, C.c_void_p, C.c_void_p, sz, C.c_char_p, sz, sz, ci]
+    emu.blosc_b200_frame_decompress.restype = ll; emu.blosc_b200_frame_decompress.argtypes = [C.c_void_p, sz, C.c_void_p, sz, ci]
+    emu.blosc_b200_frame_chunk.restype = ll; emu.blosc_b200_frame_chunk.argtypes = [C.c_void_p, sz, sz, C.POINTER(sz)]
+    n, cs = 1000003, 1 << 18
+    for kind, comp, ts, shuf in (("bench", "lz4", 4, 1), ("mixed", "lz4hc", 8, 1), ("f32", "lz4", 2, 2)):
+        src = gen(kind, n)
+        bound = emu.blosc_b200_frame_bound(n, ts, cs)
+        frame = np.full(bound + 64, 0xAA, np.uint8)
+        fb = emu.blosc_b200_frame_compress(5, shuf, ts, n, src.ctypes.data, frame.ctypes.data, bound, comp.encode(), 0, cs, 4)
+        assert fb > 0 and (frame[fb:] == 0xAA).all()
+        ccs = cs - (cs % ts if ts > 1 else 0)
+        for i in range((n + ccs - 1) // ccs):
+            cb = sz(0)
+            off = emu.blosc_b200_frame_chunk(frame.ctypes.data, fb, i, C.byref(cb))
+            piece = src[i * ccs:(i + 1) * ccs]
+            dn, out = decompress(ref, "blosc_decompress_ctx", frame[off:off + cb.value].copy(), len(piece))
+            assert dn == len(piece) and (out[:len(piece)] == piece).all(), (kind, i)
+        back = np.zeros(n + 64, np.uint8)
+        assert emu.blosc_b200_frame_decompress(frame.ctypes.data, fb, back.ctypes.data, n, 1) == n and (back[:n] == src).all()

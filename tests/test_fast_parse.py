@@ -217,3 +217,42 @@ def test_emu_frames_with_fast_parse_and_lz4hc(emu, ref, fast_env):
             assert dn == len(piece) and (out[:len(piece)] == piece).all(), (kind, i)
         back = np.zeros(n + 64, np.uint8)
         assert emu.blosc_b200_frame_decompress(frame.ctypes.data, fb, back.ctypes.data, n, 1) == n and (back[:n] == src).all()
+
+
+def _synth(rng, n):
+    """runs, noise, short periods, copies from far back, staircases, low-entropy bytes -- in random order and lengths"""
+    out = np.zeros(n, np.uint8)
+    p = 0
+    while p < n:
+        k, L = int(rng.integers(0, 6)), int(min(rng.integers(1, 5000), n - p))
+        if k == 0:
+            out[p:p + L] = rng.integers(0, 256)
+        elif k == 1:
+            out[p:p + L] = rng.integers(0, 256, L)
+        elif k == 2:
+            out[p:p + L] = np.resize(rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8), L)
+        elif k == 3 and p > 10:
+            off = int(rng.integers(1, min(p, 70000)))
+            for i in range(L):
+                out[p + i] = out[p + i - off]
+        elif k == 4:
+            out[p:p + L] = (np.arange(L) // int(rng.integers(1, 9))) % 251
+        else:
+            out[p:p + L] = rng.integers(0, 4, L)
+        p += L
+    return out
+
+
+def test_emu_fast_parse_fuzz(emu, ref, fast_env):
+    """differential fuzz (a longer run of the same generator, 8 800 cases, found nothing): random structure, sizes,
+    typesizes, filters, levels, forced block sizes, "lz4" and "lz4hc" -- the reference must decode every chunk"""
+    rng = np.random.default_rng(7)
+    for _ in range(160):
+        n = int(rng.choice([13, 100, 1000, 4097, 70001, 200003]))
+        src = _synth(rng, n)
+        ts, shuf, cl = int(rng.choice([1, 2, 3, 4, 8, 16, 32])), int(rng.integers(0, 3)), int(rng.integers(1, 10))
+        comp, bs = str(rng.choice(["lz4", "lz4hc"])), int(rng.choice([0, 0, 0, 4096, 100000]))
+        r, chunk = compress(emu, "blosc_compress_ctx", cl, shuf, ts, src, n + 16, comp, bs)
+        assert r > 0 and (chunk[r:] == 0xAA).all(), (n, ts, shuf, cl, comp, bs)
+        dn, out = decompress(ref, "blosc_decompress_ctx", chunk, n)
+        assert dn == n and (out[:n] == src).all(), (n, ts, shuf, cl, comp, bs)

@@ -54,6 +54,7 @@ extern "C" int b2_device_prepare(void) {
   CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
   CK(cudaFuncSetAttribute(encode_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TEAM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_LZ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
+  CK(cudaFuncSetAttribute(decode_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4P_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_BLOSCLZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZLIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
   CK(cudaFuncSetAttribute(decode_kernel<B2_CODEC_ZSTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, DECODE_WARPS * LZ4D_SMEM));
@@ -283,7 +284,27 @@ extern "C" int b2_launch_compact(const CompactArgs* a, b2_stream_t s) {
   return 0;
 }
 
+/* LZ4 streams are decoded by a parser / copier pair of warps (BLOSC_B200_LZ4D_PAIR=0: one warp per stream) */
+static int pair_wanted(const DecodeArgs* a) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("BLOSC_B200_LZ4D_PAIR"); env = (e && *e) ? atoi(e) != 0 : 1; }
+  return env && a->codec == B2_CODEC_LZ4;
+}
+
 extern "C" int b2_launch_decode(const DecodeArgs* a, b2_stream_t s) {
+  if (pair_wanted(a)) {
+    int ctas = a->map.nstreams;
+    const int cap = num_sms() * PAIR_CTAS_PER_SM;
+    if (ctas > cap) ctas = cap;
+    if (ctas <= 0) return 0;
+    ProfScope ps(B2_K_DECODE, s->s);
+    DecodeArgs args = *a;
+    args.queue_base = *a->queue_base_host;
+    *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas;      /* one ticket-drawing warp per CTA */
+    decode_pair_kernel<<<ctas, 64, LZ4P_SMEM, s->s>>>(args);
+    CK(cudaGetLastError());
+    return 0;
+  }
   const int wpc = DECODE_WARPS;
   const int ctas = (a->map.nstreams + wpc - 1) / wpc;
   if (ctas <= 0) return 0;

@@ -19,6 +19,7 @@
 #include "dev_inflate.cuh"
 #include "dev_lz4.cuh"
 #include "dev_lz4fast.cuh"
+#include "dev_lz4dpair.cuh"
 #include "dev_zstd.cuh"
 
 
@@ -488,6 +489,56 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_kernel(DecodeArgs a)
     mine++;
     __syncwarp();
   }
+  if (mine == 0) return;
+  __threadfence();
+  int last = 0;
+  if (lane_id() == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;
+  last = __shfl_sync(FULLMASK, last, 0);
+  if (!last) return;
+  __threadfence();
+  if (lane_id() == 0) { *a.status_out = ld_cg_i32(a.status); *a.status = 0; *a.done = 0; }
+}
+
+
+/* LZ4 chunks: one CTA of two warps per stream -- a parser that walks the tokens and a copier that owns the output
+ * (dev_lz4dpair.cuh).  The parser warp alone draws tickets, checks the size prefixes, counts finished streams and
+ * publishes the verdict, exactly as a warp of decode_kernel does. */
+#define PAIR_CTAS_PER_SM 12
+__global__ void __launch_bounds__(64) decode_pair_kernel(DecodeArgs a) {
+#ifdef SIMT_EMU
+  u8* smem = simt::g_dynsmem;
+#else
+  extern __shared__ __align__(16) u8 smem[];
+#endif
+  Lz4pSlot* slots = (Lz4pSlot*)(smem + LZ4D_RING);
+  if ((threadIdx.x >> 5) == 1) { lz4_pair_copier(smem, slots); return; }
+  int mine = 0;
+  for (;;) {
+    const int idx = next_stream(a.queue, a.queue_base, a.map);
+    if (idx < 0) break;
+    int block, len, split;
+    long long off;
+    stream_locate(a.map, idx, &block, &off, &len, &split);
+    int so = ld_i32(a.chunk + 16 + 4ll * block);
+    int cs = 0, err = 0;
+    for (int s = 0; s <= split; s++) {
+      if (so < 0 || so > a.cbytes - 4) { err = B2_ERR_BOUNDS; break; }
+      cs = ld_i32(a.chunk + so);
+      so += 4;
+      if (cs < 0 || cs > a.cbytes - so) { err = B2_ERR_BOUNDS; break; }
+      if (s < split) so += cs;
+    }
+    if (!err) {
+      u8* out = a.out + (off - a.out_shift);
+      const u8* src = a.chunk + so;
+      if (cs == len) warp_copy_bytes(out, src, len);                    /* stored raw, blosc.c:773-776 */
+      else if (lz4_pair_parse(src, cs, out, len, slots) != len) err = B2_ERR_CODEC;   /* blosc.c:778-782 */
+    }
+    if (err && lane_id() == 0) atomicMin(a.status, err);
+    mine++;
+    __syncwarp();
+  }
+  lz4_pair_quit(slots);
   if (mine == 0) return;
   __threadfence();
   int last = 0;

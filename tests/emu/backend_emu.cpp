@@ -135,7 +135,20 @@ int b2_launch_compact(const CompactArgs* a, b2_stream_t) {
   return 0;
 }
 
+static int g_lz4d_pair = 1;
+void emu_set_lz4d_pair(int on) { g_lz4d_pair = on; }
+
 int b2_launch_decode(const DecodeArgs* a, b2_stream_t) {
+  if (g_lz4d_pair && a->codec == B2_CODEC_LZ4) {
+    int ctas = a->map.nstreams < 3 ? a->map.nstreams : 3;      /* few CTAs: every pair goes through several streams */
+    if (ctas <= 0) return 0;
+    g_launches++;
+    DecodeArgs args = *a;
+    args.queue_base = *a->queue_base_host;
+    *a->queue_base_host += (unsigned)a->map.nstreams + (unsigned)ctas;
+    simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(64), LZ4P_SMEM, [&] { decode_pair_kernel(args); });
+    return 0;
+  }
   const int wpc = DECODE_WARPS;
   const int ctas = (a->map.nstreams + wpc - 1) / wpc;
   if (ctas <= 0) return 0;
@@ -191,6 +204,19 @@ int emu_lz4_decode(const unsigned char* src, int csize, unsigned char* dst, int 
   int result = 0;
   simt::launch(simt::Dim3(1), simt::Dim3(32), LZ4D_SMEM, [&] {
     int r = lz4_decode_warp(src, csize, dst, cap, simt::g_dynsmem);
+    if ((threadIdx.x & 31) == 13) result = r;
+  });
+  return result;
+}
+/* the same stream through a parser / copier pair */
+int emu_lz4_decode_pair(const unsigned char* src, int csize, unsigned char* dst, int cap) {
+  int result = 0;
+  simt::launch(simt::Dim3(1), simt::Dim3(64), LZ4P_SMEM, [&] {
+    unsigned char* smem = simt::g_dynsmem;
+    Lz4pSlot* slots = (Lz4pSlot*)(smem + LZ4D_RING);
+    if ((threadIdx.x >> 5) == 1) { lz4_pair_copier(smem, slots); return; }
+    int r = lz4_pair_parse(src, csize, dst, cap, slots);
+    lz4_pair_quit(slots);
     if ((threadIdx.x & 31) == 13) result = r;
   });
   return result;

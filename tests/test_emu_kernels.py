@@ -258,3 +258,45 @@ def test_lz4_packed_table_is_bit_exact(emu, orc, monkeypatch):
         r1, c1 = compress(emu, "blosc_compress_ctx", 5, 1, ts, src, n + 16, "lz4")
         r2, c2 = compress(orc, "orc_compress_ctx", 5, 1, ts, src, n + 16, "lz4")
         assert r1 == r2 and (c1[:r1] == c2[:r2]).all(), (kind, n, ts)
+
+
+def test_lz4_pair_decoder_equals_single_warp_decoder(emu, orc):
+    """dev_lz4dpair.cuh (parser warp + copier warp per stream) against lz4_decode_warp and the oracle: same bytes on valid
+    streams of every kind and size, same accept / reject verdict (and same bytes when accepted) on damaged ones."""
+    emu.emu_lz4_decode_pair.restype = ci
+    rng = np.random.default_rng(5)
+    for kind in ("bench", "text", "zeros", "lowent", "mixed", "rand", "i32", "f32"):
+        for n in (13, 200, 4097, 70001, 300000):
+            src = gen(kind, n, seed=n & 3)
+            a = np.zeros(n + n // 255 + 64, np.uint8)
+            ra = orc.orc_lz4_compress_fast(ptr(src), ptr(a), ci(n), ci(len(a)), ci(1 + (n & 7)))
+            assert ra > 0
+            o1, o2 = np.full(n + 8, 0x55, np.uint8), np.full(n + 8, 0x55, np.uint8)
+            assert emu.emu_lz4_decode_pair(ptr(a), ci(ra), ptr(o2), ci(n)) == n and (o2[:n] == src).all() and (o2[n:] == 0x55).all()
+            # wrong capacity, truncated input
+            assert emu.emu_lz4_decode_pair(ptr(a), ci(ra), ptr(o2), ci(n - 1)) == emu.emu_lz4_decode(ptr(a), ci(ra), ptr(o1), ci(n - 1))
+            assert emu.emu_lz4_decode_pair(ptr(a), ci(ra - 1), ptr(o2), ci(n)) == emu.emu_lz4_decode(ptr(a), ci(ra - 1), ptr(o1), ci(n))
+            for trial in range(12):
+                c = a[:ra].copy()
+                for pos in rng.integers(0, ra, 1 + trial % 3):
+                    c[pos] = (0, 0xF0, 0x0F, int(rng.integers(0, 256)))[trial % 4]
+                o1[:] = 0x55; o2[:] = 0x55
+                d1 = emu.emu_lz4_decode(ptr(c), ci(ra), ptr(o1), ci(n))
+                d2 = emu.emu_lz4_decode_pair(ptr(c), ci(ra), ptr(o2), ci(n))
+                assert d1 == d2, (kind, n, trial, d1, d2)
+                if d1 >= 0:
+                    assert (o1[:n] == o2[:n]).all()
+                assert (o2[n:] == 0x55).all()
+
+
+def test_chunks_decode_with_one_warp_per_stream_too(emu, orc):
+    """the single-warp LZ4 decoder stays available (BLOSC_B200_LZ4D_PAIR=0 in the product)"""
+    emu.emu_set_lz4d_pair(0)
+    try:
+        for kind, n, ts, shuf in (("bench", 1 << 20, 4, 1), ("mixed", 300001, 8, 2), ("text", 70001, 1, 0)):
+            src = gen(kind, n)
+            cb, chunk = compress(orc, "orc_compress_ctx", 5, shuf, ts, src, n + 16, "lz4")
+            dn, out = decompress(emu, "blosc_decompress_ctx", chunk, n)
+            assert dn == n and (out[:n] == src).all()
+    finally:
+        emu.emu_set_lz4d_pair(1)

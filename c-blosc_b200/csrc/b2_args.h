@@ -139,6 +139,7 @@ typedef struct DecodeArgs {
   unsigned* queue_base_host;
   int* done;             /* zero-initialised count of finished streams */
   int* status_out;       /* the last warp publishes the verdict here and zeroes the three words above */
+  int many;              /* other calls are running on this device: streams per SM matter more than latency */
 } DecodeArgs;
 
 #ifdef __cplusplus

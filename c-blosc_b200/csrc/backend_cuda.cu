@@ -284,11 +284,16 @@ extern "C" int b2_launch_compact(const CompactArgs* a, b2_stream_t s) {
   return 0;
 }
 
-/* LZ4 streams are decoded by a parser / copier pair of warps (BLOSC_B200_LZ4D_PAIR=0: one warp per stream) */
+/* LZ4 streams can be decoded by a parser / copier pair of warps per stream (dev_lz4dpair.cuh).  Like the encoder's
+ * team mode it shortens the critical path of a hard stream and costs throughput where every stream is hard (a
+ * descriptor per sequence on the general path): measured on the bench.c planes 0.75 -> 0.53 ms at typesize 4
+ * (fast-parse chunks 0.86 -> 0.56, lz4hc 2.03 -> 1.21), but 1.04 -> 1.22 ms at typesize 2 and 0.95 -> 1.07 at typesize 8.
+ * Default: blocks of four splits when the call has the device to itself; BLOSC_B200_LZ4D_PAIR=0 / 1 forces it. */
 static int pair_wanted(const DecodeArgs* a) {
-  static int env = -1;
-  if (env < 0) { const char* e = getenv("BLOSC_B200_LZ4D_PAIR"); env = (e && *e) ? atoi(e) != 0 : 1; }
-  return env && a->codec == B2_CODEC_LZ4;
+  static int env = -2;
+  if (env == -2) { const char* e = getenv("BLOSC_B200_LZ4D_PAIR"); env = (e && *e) ? (atoi(e) != 0) : -1; }
+  if (a->codec != B2_CODEC_LZ4) return 0;
+  return env >= 0 ? env : (a->map.nsplits == 4 && !a->many);
 }
 
 extern "C" int b2_launch_decode(const DecodeArgs* a, b2_stream_t s) {

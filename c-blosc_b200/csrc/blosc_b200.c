@@ -785,6 +785,7 @@ static int decode_blocks(b2_ws* w, const b2_hdr* h, int codec, const uint8_t* d_
   da.codec = codec; da.status = w->d_result + B2_R_STATUS; da.queue = w->d_result + B2_R_QUEUE;
   da.queue_base_host = &w->queue_base;
   da.done = w->d_result + B2_R_DONE; da.status_out = w->d_result + B2_R_STATUS_OUT;
+  da.many = ws_busy(w->dev) > 1;
   if (b2_launch_decode(&da, w->stream)) { ws_reset_counters(w); return -1; }
   if (doshuffle || dobitshuffle) {
     fa.src = d_codec_out; fa.dst = d_out; fa.nbytes = span; fa.blocksize = bs; fa.typesize = ts;

@@ -15,7 +15,8 @@ cap() {  # name kernel-regex spec env skip mangled-name-substring
   case "$1" in encode_team|parse) ;; *) rm -f gpurun_out/${T}_$1.ncu-rep ;; esac     # gpurun_out/ travels back only below 64 MiB
 }
 cap encode_team encode_team_kernel lz4:1:4 X=1 3 encode_team_kernel
-cap decode_lz4 decode_kernel lz4:1:4 X=1 3 decode_kernelILi1E
+cap decode_pair decode_pair_kernel lz4:1:4 X=1 3 decode_pair_kernel
+cap decode_lz4 decode_kernel lz4:1:4 BLOSC_B200_LZ4D_PAIR=0 3 decode_kernelILi1E
 cap filter_shuffle filter_kernel lz4:1:4 X=1 6 filter_kernelILi4E
 cap filter_unshuffle filter_kernel lz4:1:4 X=1 7 filter_kernelILi4E
 cap compact compact_kernel lz4:1:4 X=1 3 compact_kernel

@@ -385,7 +385,7 @@ def measure_traffic(workload):
     workload: a separate short `ncu` run of scripts/kbench.py (counters only -- nothing timed under the profiler)."""
     comp_name, shuf, ts, clevel, nbytes = WORKLOADS[workload]
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
-           "regex:encode_kernel|encode_team_kernel|decode_kernel", "-s", "6", "-c", "2", "--csv", sys.executable,
+           "regex:encode_kernel|encode_team_kernel|decode_kernel|decode_pair_kernel", "-s", "6", "-c", "2", "--csv", sys.executable,
            os.path.join(ROOT, "scripts", "kbench.py"), "ncu", f"{comp_name}:{shuf}:{ts}"]
     try:
         env = dict(os.environ, KBENCH_STEPS="1")

@@ -569,8 +569,7 @@ def main():
             e.dist.destroy_process_group()
         return
 
-    config = chunk_config(head_wl)
-    config["host_buffers"] = head["e2e"].pop("host_buffers")
+    config = chunk_config(head_wl)              # identical in both arms (the driver compares them); host placement is under e2e
     line = {"metric": METRIC, "value": head["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config, "compress_gbs": head["compress_gbs"], "decompress_gbs": head["decompress_gbs"],

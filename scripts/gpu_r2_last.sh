@@ -13,3 +13,6 @@ cap() {
 }
 cap decode_pair decode_pair_kernel lz4:1:4 X=1 3 decode_pair_kernel
 cap decode_lz4 decode_kernel lz4:1:4 BLOSC_B200_LZ4D_PAIR=0 3 decode_kernelILi1E
+BLOSC_B200_LZ4_TEAM=0 timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python scripts/sanitize_small.py > gpurun_out/${T}_racecheck_noteam.log 2>&1; echo "racecheck (team encoder off, pair decoder on) rc=$?"; tail -2 gpurun_out/${T}_racecheck_noteam.log
+BLOSC_B200_PARSE=fast timeout 300 python scripts/kbench.py fast lz4:1:4 lz4:1:8 2>&1 | tee gpurun_out/${T}_kbench_fast.log | cut -c1-300
+timeout 300 python scripts/kbench.py exact lz4:1:4 lz4:1:2 lz4:1:8 lz4:1:16 blosclz:2:8 lz4hc:1:4 2>&1 | tee gpurun_out/${T}_kbench_exact.log | cut -c1-300

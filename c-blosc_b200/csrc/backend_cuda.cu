@@ -259,7 +259,7 @@ extern "C" int b2_launch_fast(const FastArgs* a, b2_stream_t s) {
     CK(cudaGetLastError());
   }
   {
-    const int ctas = (a->map.nstreams + FSCAN_WARPS * 32 - 1) / (FSCAN_WARPS * 32);
+    const int ctas = (a->map.nstreams + FSCAN_WARPS - 1) / FSCAN_WARPS;
     ProfScope ps(B2_K_SCAN, s->s);
     fscan_kernel<<<ctas, FSCAN_WARPS * 32, 0, s->s>>>(*a);
     CK(cudaGetLastError());

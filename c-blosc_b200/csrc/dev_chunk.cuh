@@ -309,30 +309,28 @@ __global__ void __launch_bounds__(B2_FAST_WIN_MAX / FAST_SEG, 3) parse_kernel(Fa
   }
 }
 
-/* One THREAD per stream: scan of its segment records (pending literals, continued matches, output offsets, compressed
- * size); the warp that finishes the last streams runs the block scan, exactly as in encode_kernel. */
-#define FSCAN_WARPS 2
+/* One warp per stream: scan of its segment records (pending literals, continued matches, output offsets, compressed
+ * size); the warp that finishes the last stream runs the block scan, exactly as in encode_kernel. */
+#define FSCAN_WARPS 4
 __global__ void __launch_bounds__(FSCAN_WARPS * 32) fscan_kernel(FastArgs a) {
   const int lane = lane_id();
   const int nfs = a.map.nfull * a.map.nsplits;
-  const int idx = (int)blockIdx.x * (FSCAN_WARPS * 32) + (int)threadIdx.x;
   int mine = 0;
-  if (idx < a.map.nstreams) {
+  for (int idx = (int)blockIdx.x * FSCAN_WARPS + (int)(threadIdx.x >> 5); idx < a.map.nstreams; idx += (int)gridDim.x * FSCAN_WARPS) {
     int block, len, split;
     long long off;
     stream_locate(a.map, idx, &block, &off, &len, &split);
     int ptail = 0;
     int c = lz4f_stream_scan(a.segs + (long long)idx * a.segs_full, idx < nfs ? a.segs_full : a.segs_left, len, &ptail);
     if (c >= len) c = len;                         /* blosc.c:705-714: incompressible split is stored raw */
-    a.csizes[idx] = c; a.needs[idx] = c; a.ptail[idx] = ptail;
-    mine = 1;
+    if (lane == 0) { a.csizes[idx] = c; a.needs[idx] = c; a.ptail[idx] = ptail; }
+    mine++;
+    __syncwarp();
   }
-  __syncwarp();
-  const int wmine = __popc(__ballot_sync(FULLMASK, mine));
-  if (wmine == 0) return;
+  if (mine == 0) return;
   __threadfence();
   int last = 0;
-  if (lane == 0) last = atomicAdd(a.done, wmine) + wmine == a.map.nstreams;
+  if (lane == 0) last = atomicAdd(a.done, mine) + mine == a.map.nstreams;
   last = __shfl_sync(FULLMASK, last, 0);
   if (!last) return;
   __threadfence();

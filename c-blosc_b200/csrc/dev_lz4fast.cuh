@@ -373,57 +373,53 @@ DEV void lz4f_parse_lane(const FastView& v, const int n, const u16* __restrict__
 DEV int fast_ml_ext(int ml) { return ml - 4 >= 15 ? 1 + (ml - 4 - 15) / 255 : 0; }
 
 /* ---- per-stream scan of the segment records: pending literals, continued matches, output offsets, size ----
- * Run by ONE THREAD per stream (32 streams per warp) once the chunk has been parsed: the walk over the K records is
- * a sequential state machine of a few instructions per record; the records of four steps are requested together so
- * that the walk does not wait for L2 on every one.  A segment that is ONE match over all its bytes, with the offset of
- * the match that ends the segment before it, is swallowed: that match simply goes on.  Returns the size of the merged
- * LZ4 block; *ptail = literals after the stream's last match. */
-DEV void fast_rec_fields(const FastSeg* r, u32& x0, u32& x1, u32& x2) {
-#ifdef SIMT_EMU
-  x0 = (u32)r->nbytes | ((u32)r->l1 << 16); x1 = (u32)r->tail | ((u32)r->lt << 16); x2 = (u32)r->lm | ((u32)r->lo << 16);
-#else
-  const uint4 q = __ldcg((const uint4*)r);        /* written by the parse kernel */
-  x0 = q.x; x1 = q.y; x2 = q.z;
-#endif
-}
+ * Run by one warp once every segment of the stream has been parsed; the walk over the K records is sequential
+ * (a few instructions per record, every lane computes the same state; records are fetched 32 at a time and
+ * broadcast by shuffles).  A segment that is ONE match over all its bytes, with the offset of the match that
+ * ends the segment before it, is swallowed: that match simply goes on.  Returns the size of the merged LZ4
+ * block (uniform); *ptail = literals after the stream's last match. */
 DEV int lz4f_stream_scan(FastSeg* segs, const int K, const int n, int* ptail) {
+  const int lane = lane_id();
   long long pos = 0;
   int carry = 0;                      /* literals since the last match */
   int head = -1, head_total = 0, head_lo = 0;   /* open sequence: last match of segment `head` ends at a segment boundary */
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    u32 f0[4], f1[4], f2[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      f0[j] = 0; f1[j] = 0; f2[j] = 0;
-      if (k0 + j < K) fast_rec_fields(&segs[k0 + j], f0[j], f1[j], f2[j]);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    u32 r0 = 0, r1 = 0, r2 = 0;
+    if (k0 + lane < K) {
+#ifdef SIMT_EMU
+      const FastSeg* r = &segs[k0 + lane];
+      r0 = (u32)r->nbytes | ((u32)r->l1 << 16); r1 = (u32)r->tail | ((u32)r->lt << 16); r2 = (u32)r->lm | ((u32)r->lo << 16);
+#else
+      const uint4 q = __ldcg((const uint4*)&segs[k0 + lane]);     /* written by other SMs during this launch */
+      r0 = q.x; r1 = q.y; r2 = q.z;
+#endif
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int k = k0 + j;
-      if (k >= K) break;
-      const u32 x0 = f0[j], x1 = f1[j], x2 = f2[j];
+    const int cnt = K - k0 < 32 ? K - k0 : 32;
+    for (int j = 0; j < cnt; j++) {
+      const u32 x0 = __shfl_sync(FULLMASK, r0, j), x1 = __shfl_sync(FULLMASK, r1, j), x2 = __shfl_sync(FULLMASK, r2, j);
       const int nb = (int)(x0 & 0xffffu), l1 = (int)(x0 >> 16), tl = (int)(x1 & 0xffffu), lt = (int)(x1 >> 16);
       const int lm = (int)(x2 & 0xffffu), lo = (int)(x2 >> 16);
+      const int k = k0 + j;
       const int a = k * FAST_SEG, len = (a + FAST_SEG < n ? a + FAST_SEG : n) - a;
       if (nb == 0) {                                                   /* all literals */
-        if (head >= 0) { pos += fast_ml_ext(head_total); segs[head].run = (u32)head_total; head = -1; }
+        if (head >= 0) { pos += fast_ml_ext(head_total); if (lane == 0) segs[head].run = (u32)head_total; head = -1; }
         carry += tl;
         continue;
       }
       if (head >= 0 && lt == 0 && l1 == 0 && tl == 0 && lm == len && lo == head_lo) {   /* swallowed */
         head_total += len;
-        segs[k].dst = 0xffffffffu;
+        if (lane == 0) segs[k].dst = 0xffffffffu;
         continue;
       }
-      if (head >= 0) { pos += fast_ml_ext(head_total); segs[head].run = (u32)head_total; head = -1; }
+      if (head >= 0) { pos += fast_ml_ext(head_total); if (lane == 0) segs[head].run = (u32)head_total; head = -1; }
       const int lit = carry + l1;
-      segs[k].dst = (u32)pos; segs[k].pin = (u32)carry;
+      if (lane == 0) { segs[k].dst = (u32)pos; segs[k].pin = (u32)carry; }
       pos += 1 + fast_lit_ext(lit) + lit + (nb - 1);
       if (tl == 0) { head = k; head_total = lm; head_lo = lo; carry = 0; }
-      else { pos += fast_ml_ext(lm); segs[k].run = (u32)lm; carry = tl; }
+      else { pos += fast_ml_ext(lm); if (lane == 0) segs[k].run = (u32)lm; carry = tl; }
     }
   }
-  if (head >= 0) { pos += fast_ml_ext(head_total); segs[head].run = (u32)head_total; }
+  if (head >= 0) { pos += fast_ml_ext(head_total); if (lane == 0) segs[head].run = (u32)head_total; }
   pos += 1 + fast_lit_ext(carry) + carry;
   *ptail = carry;
   return pos > 0x7fffffffll ? 0x7fffffff : (int)pos;

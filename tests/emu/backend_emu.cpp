@@ -114,7 +114,7 @@ int b2_launch_fast(const FastArgs* a, b2_stream_t) {
   args.queue_base = *a->queue_base_host;
   *a->queue_base_host += (unsigned)njobs + (unsigned)ctas;
   simt::launch(simt::Dim3((unsigned)ctas), simt::Dim3(a->threads), (size_t)a->win_bytes + 64, [&] { parse_kernel(args); });
-  simt::launch(simt::Dim3((unsigned)((a->map.nstreams + FSCAN_WARPS * 32 - 1) / (FSCAN_WARPS * 32))), simt::Dim3(FSCAN_WARPS * 32), 0, [&] { fscan_kernel(args); });
+  simt::launch(simt::Dim3(2), simt::Dim3(FSCAN_WARPS * 32), 0, [&] { fscan_kernel(args); });
   return 0;
 }
 

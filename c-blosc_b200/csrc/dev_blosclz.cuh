@@ -318,7 +318,56 @@ DEV int blz_decode_warp(const u8* __restrict__ in, const int length, u8* out, co
   int ip = 0, op = 0;
   if (length == 0) return 0;
   u32 ctrl = in[ip++] & 31u;
+  const int lane = lane_id();
+  int dense_skip = 0, dense_back = 0;
   for (;;) {
+    /* ---- dense path: a chain of short near matches, one per lane ----
+     * The byte-planes of shuffled data decode to long chains of 2-byte tokens (ctrl with 3 <= len <= 8, 13-bit
+     * distance, no length extension, no far distance: blosclz.c:699-727).  If the token at hand is of that form the
+     * next one starts two bytes later, so lane l looks at the bytes ip-1+2l, ip+2l and the leading run of lanes that
+     * all see this form are real tokens.  A prefix sum of the lengths places every match; matches whose source lies
+     * entirely before the step's first output byte are independent and every lane copies its own. */
+    if (dense_skip > 0) dense_skip--;
+    else if (ctrl >= 32 && ip + 66 <= length && (long long)op + 256 <= maxout) {
+      const u32 c = lane == 0 ? ctrl : (u32)in[ip - 1 + 2 * lane];
+      const u32 code = in[ip + 2 * lane];
+      const bool simple = c >= 32u && (c >> 5) != 7u && !((c & 31u) == 31u && code == 255u);
+      const int len = (int)(c >> 5) + 2;                                   /* (ctrl >> 5) - 1 + 3 */
+      const int dist = (int)((c & 31u) << 8) + (int)code + 1;
+      const unsigned okm = __ballot_sync(FULLMASK, simple);
+      int cnt = okm == FULLMASK ? 32 : __ffs((int)~okm) - 1;
+      int incl = lane < cnt ? len : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULLMASK, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int dst = op + incl - len, ref = dst - dist;
+      /* a source that touches this step's own output (or is in front of the buffer: the serial code below gives the
+       * verdict) ends the run; 8 bytes of slack for the word-wise read */
+      const unsigned bad = __ballot_sync(FULLMASK, lane < cnt && (dist < incl + 8 || ref < 0));
+      if (bad) cnt = __ffs((int)bad) - 1;
+      if (cnt >= 4) {
+        const int total = __shfl_sync(FULLMASK, incl, cnt - 1);
+        if (lane < cnt) {
+          const u32 v0 = ld_u32(out + ref), v1 = ld_u32(out + ref + 4);
+          u8* o = out + dst;
+          o[0] = (u8)v0; o[1] = (u8)(v0 >> 8); o[2] = (u8)(v0 >> 16);
+          if (len > 3) o[3] = (u8)(v0 >> 24);
+          if (len > 4) o[4] = (u8)v1;
+          if (len > 5) o[5] = (u8)(v1 >> 8);
+          if (len > 6) o[6] = (u8)(v1 >> 16);
+          if (len > 7) o[7] = (u8)(v1 >> 24);
+        }
+        __syncwarp();
+        op += total; ip += 2 * cnt;
+        ctrl = in[ip - 1];
+        dense_back = 0;
+        continue;
+      }
+      dense_back = dense_back < 8 ? dense_back + 1 : 8;                    /* not that kind of data right here: back off */
+      dense_skip = dense_back;
+    }
     if (ctrl >= 32) {
       long long len = (long long)(ctrl >> 5) - 1;
       int ofs = (int)(ctrl & 31u) << 8;

@@ -300,3 +300,32 @@ def test_chunks_decode_with_one_warp_per_stream_too(emu, orc):
             assert dn == n and (out[:n] == src).all()
     finally:
         emu.emu_set_lz4d_pair(1)
+
+
+def test_blosclz_dense_path_on_corrupted_chains(emu, orc):
+    """The dense BloscLZ decoder path (up to 32 two-byte match tokens per step) on the byte-planes of shuffled bench.c
+    data: the oracle's bytes on the valid streams, and the oracle's accept / reject verdict (and bytes, when accepted) when
+    single bytes of the stream are damaged -- distances reaching before the block, overlapping sources, far-distance and
+    length-extension markers appearing in the middle of a chain."""
+    rng = np.random.default_rng(17)
+    words = gen("bench", 1 << 19).view(np.uint32)
+    n = len(words)
+    for b in range(3):
+        plane = ((words >> (8 * b)) & 0xff).astype(np.uint8)
+        a = np.zeros(n + 64, np.uint8)
+        ra = orc.orc_blosclz_compress(ci(5), ptr(plane), ci(n), ptr(a), ci(n), ci(1))
+        if ra <= 0:
+            continue
+        o = np.zeros(n + 8, np.uint8)
+        assert emu.emu_blz_decode(ptr(a), ci(ra), ptr(o), ci(n)) == n and (o[:n] == plane).all() and (o[n:] == 0).all()
+        for trial in range(60):
+            c = a[:ra].copy()
+            for pos in rng.integers(1, ra, 1 + trial % 3):
+                c[pos] = (0, 0xFF, 0xE0 | int(rng.integers(0, 32)), 0x3F, int(rng.integers(0, 256)))[trial % 5]
+            o1 = np.zeros(n + 16, np.uint8); o2 = np.zeros(n + 16, np.uint8)
+            d1 = orc.orc_blosclz_decompress(ptr(c), ci(ra), ptr(o1), ci(n))
+            d2 = emu.emu_blz_decode(ptr(c), ci(ra), ptr(o2), ci(n))
+            assert (d1 <= 0) == (d2 <= 0) or d1 == d2, (b, trial, d1, d2)
+            if d1 > 0 and d1 == d2:
+                assert (o1[:d1] == o2[:d1]).all(), (b, trial)
+            assert (o2[n:] == 0).all()

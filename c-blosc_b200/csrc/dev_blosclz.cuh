@@ -336,6 +336,11 @@ DEV int blz_decode_warp(const u8* __restrict__ in, const int length, u8* out, co
       const int dist = (int)((c & 31u) << 8) + (int)code + 1;
       const unsigned okm = __ballot_sync(FULLMASK, simple);
       int cnt = okm == FULLMASK ? 32 : __ffs((int)~okm) - 1;
+      if (cnt < 4) {                                                       /* not worth a step: straight to the token machine */
+        dense_back = dense_back < 8 ? dense_back + 1 : 8;
+        dense_skip = dense_back;
+        goto serial;
+      }
       int incl = lane < cnt ? len : 0;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -368,6 +373,7 @@ DEV int blz_decode_warp(const u8* __restrict__ in, const int length, u8* out, co
       dense_back = dense_back < 8 ? dense_back + 1 : 8;                    /* not that kind of data right here: back off */
       dense_skip = dense_back;
     }
+  serial:
     if (ctrl >= 32) {
       long long len = (long long)(ctrl >> 5) - 1;
       int ofs = (int)(ctrl & 31u) << 8;

@@ -337,7 +337,7 @@ DEV int blz_decode_warp(const u8* __restrict__ in, const int length, u8* out, co
       const unsigned okm = __ballot_sync(FULLMASK, simple);
       int cnt = okm == FULLMASK ? 32 : __ffs((int)~okm) - 1;
       if (cnt < 4) {                                                       /* not worth a step: straight to the token machine */
-        dense_back = dense_back < 8 ? dense_back + 1 : 8;
+        dense_back = dense_back < 32 ? dense_back + dense_back / 2 + 1 : 32;
         dense_skip = dense_back;
         goto serial;
       }
@@ -370,7 +370,7 @@ DEV int blz_decode_warp(const u8* __restrict__ in, const int length, u8* out, co
         dense_back = 0;
         continue;
       }
-      dense_back = dense_back < 8 ? dense_back + 1 : 8;                    /* not that kind of data right here: back off */
+      dense_back = dense_back < 32 ? dense_back + dense_back / 2 + 1 : 32;   /* not that kind of data right here: back off */
       dense_skip = dense_back;
     }
   serial:
